@@ -1,0 +1,108 @@
+/* nk_b200.h -- C ABI of the B200-native Nystrom-Koopman hot path (libnkb200.so).
+ *
+ * Drop-in boundary: these entry points are what a binding of the reference estimator
+ * (LCSL/nys-koop-lqr, regressors.py::KoopmanNystromRegressor) calls instead of numpy/scipy/sklearn.
+ * Every function cites the reference lines it replaces.  Conventions:
+ *   - return value: 0 = ok, <0 = error (NK_E_*); nk_last_error_string() gives the text.  No exceptions.
+ *   - all matrix pointers are CALLER-OWNED DEVICE pointers to IEEE float64, row-major with an explicit
+ *     leading dimension (elements) unless a parameter is documented as "host".
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); asynchronous failures
+ *     surface at the next synchronising call.  A handle is bound to one device and is not thread-safe.
+ *   - there is NO CPU fallback: every function fails with NK_E_CUDA when no sm_100 device is usable.
+ */
+#ifndef NK_B200_H
+#define NK_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nk_handle nk_handle;
+
+enum { NK_OK = 0, NK_E_INVALID = -1, NK_E_CUDA = -2, NK_E_NOT_SPD = -3, NK_E_NOMEM = -4, NK_E_STATE = -5 };
+enum { NK_KERNEL_RBF = 0, NK_KERNEL_MATERN52 = 1 };   /* sklearn RBF / Matern(nu=2.5): regressors.py:15-26 */
+
+int nk_version(void);
+int nk_create(nk_handle **out, int device);
+int nk_destroy(nk_handle *h);
+const char *nk_last_error_string(nk_handle *h);   /* h may be NULL: last creation error */
+int nk_device_sm_count(nk_handle *h);
+
+/* ---- fused kernel lift + data-sample Grams  (regressors.py:141-142 lift; :147,151,153,162,164 Grams) ----
+ * Streaming form: begin(landmarks, kernel) -> update(sample block)* -> finalize(outputs).
+ *   Z (m,d) landmarks; inv_ls (d) = 1/length_scale per state dimension (device); kind = NK_KERNEL_*;
+ *   chunk = samples per on-chip feature chunk (0 = default 512; rounded to a multiple of 128).
+ * update: X (n,d+p) rows [x_t | u_t] (controls are the LAST p columns, regressors.py:123-126), Y (n,d) = x_{t+1}.
+ * finalize writes (or adds to, if accumulate != 0):
+ *   Gxx = Phi_x Phi_x^T (m,m)   Gyx = Phi_y Phi_x^T (m,m)   Gyy = Phi_y Phi_y^T (m,m)
+ *   Gxu = Phi_x U (m,p)         Gyu = Phi_y U (m,p)         Guu = U^T U (p,p)      GYy = Y^T Phi_y^T (d,m)
+ * with Phi_x = k(Z, X_state) and Phi_y = k(Z, Y), both (m,n) and never materialised.  Any output may be NULL. */
+int nk_gram_begin(nk_handle *h, const double *Z, long long ldz, int m, int d, int p,
+                  const double *inv_ls, int kind, int chunk, void *stream);
+int nk_gram_update(nk_handle *h, const double *X, long long ldx, const double *Y, long long ldy,
+                   long long n, void *stream);
+int nk_gram_finalize(nk_handle *h, double *Gxx, long long ld_gxx, double *Gyx, long long ld_gyx,
+                     double *Gyy, long long ld_gyy, double *Gxu, long long ld_gxu, double *Gyu, long long ld_gyu,
+                     double *Guu, long long ld_guu, double *GYy, long long ld_gYy, int accumulate, void *stream);
+/* executed FP64 flops of the last update (for roofline accounting), and launches issued so far */
+double nk_gram_last_executed_flops(nk_handle *h);
+long long nk_launch_count(nk_handle *h);
+
+/* ---- landmark kernel matrix K_zz = k(Z,Z)  (regressors.py:139,143,144,174); diagonal is exactly 1 ---- */
+int nk_kzz(nk_handle *h, const double *Z, long long ldz, int m, int d, const double *inv_ls, int kind,
+           double *Kzz, long long ldk, void *stream);
+
+/* ---- kernel cross matrix K = k(Z, X): (m, N) row-major from X (N, d) rows  (regressors.py:176) ---- */
+int nk_kernel_cross(nk_handle *h, const double *Z, long long ldz, int m, int d, const double *inv_ls, int kind,
+                    const double *X, long long ldx, long long N, double *K, long long ldk, void *stream);
+
+/* ---- dense building blocks (all DMMA): C = alpha*op(A)*op(B) + beta*C, row-major ----
+ * transa/transb: 0 = as stored, 1 = transposed.  A is (M,K) after op, B is (K,N) after op. */
+int nk_gemm(nk_handle *h, int transa, int transb, int M, int N, int K, double alpha, const double *A, long long lda,
+            const double *B, long long ldb, double beta, double *C, long long ldc, void *stream);
+/* Cholesky A = L L^T in place (lower triangle; the strict upper triangle is zeroed). info (host int*) receives 0 or
+ * the 1-based index of the first non-positive pivot; the call synchronises the stream to read it. */
+int nk_potrf(nk_handle *h, int n, double *A, long long lda, int *info, void *stream);
+/* B <- L^-1 B (trans=0) or L^-T B (trans=1), L lower (n,n), B (n,nrhs) */
+int nk_trsm_lower(nk_handle *h, int trans, int n, int nrhs, const double *L, long long ldl, double *B, long long ldb, void *stream);
+/* symmetric principal square root S = K^(1/2) and S^-1 of an SPD matrix (scipy.linalg.sqrtm at regressors.py:140,163,175
+ * and the solves against it at :152,153,177).  lambda_min_bound > 0: a lower bound on the smallest eigenvalue (the
+ * jitter 1e-6 for K_mm).  iters (host int*, may be NULL) receives the Newton-Schulz iteration count. */
+int nk_sym_sqrt(nk_handle *h, int n, const double *K, long long ldk, double lambda_min_bound,
+                double *S, long long lds, double *Sinv, long long ldsi, int *iters, void *stream);
+
+/* ---- Grams -> Koopman matrices  (regressors.py:147-169) ----
+ * inner = [[Gxx + gn*Kmm, Gxu],[Gxu^T, Guu + gn*I]],  G = S^-1 [Gyx|Gyu] inner^-1 blkdiag(Kzz S^-1, I_p)
+ * A = G[:, :m], B = G[:, m:];  C = GYy (gn*Kmm + Gyy)^-1 S;  W = C G;  Kmm = Kzz + jitter*I.
+ * Outputs: A (m,m), B (m,p), C (d,m), W (d,m+p).  info (host): 0, or 1/2 if the first/second system is not SPD. */
+int nk_solve_abc(nk_handle *h, int m, int p, int d, double gamma_n, double jitter,
+                 const double *Gxx, const double *Gyx, const double *Gyy, const double *Gxu, const double *Gyu,
+                 const double *Guu, const double *GYy, const double *Kzz, const double *S, const double *Sinv,
+                 double *A, double *B, double *C, double *W, int *info, void *stream);
+
+/* ---- lift  phi = S^-1 k(Z, X)  (regressors.py:171-178): X (N,d) rows -> Phi (m,N); PhiT (N,m) is the same data
+ * transposed (either output may be NULL).  N is limited by scratch memory (N*(m+d+2) doubles); callers chunk. ---- */
+int nk_lift(nk_handle *h, const double *Z, long long ldz, int m, int d, const double *inv_ls, int kind,
+            const double *Sinv, long long ldsi, const double *X, long long ldx, long long N,
+            double *Phi, long long ldphi, double *PhiT, long long ldphit, void *stream);
+
+/* ---- predict (regressors.py:48-55): Yhat (N,d) = (W [phi(X_state); U])^T for X_aug (N, d+p) rows, W (d, m+p) ---- */
+int nk_predict(nk_handle *h, const double *Z, long long ldz, int m, int d, int p, const double *inv_ls, int kind,
+               const double *Sinv, long long ldsi, const double *W, long long ldw, const double *X_aug, long long ldx,
+               long long N, double *Yhat, long long ldy, void *stream);
+
+/* ---- batched open-loop rollout (benchmark_lqr_cloth.py:18-36 and its two copies in _classic.py:23-41, _hjb.py:23-44) ----
+ * Trajectory-major storage (one row per trajectory):  for each of nb trajectories
+ *     yhat_0 = C z_0;  z_{i+1} = A z_i + B u_i,  yhat_{i+1} = C z_{i+1},  i = 0..T-2   (serial in i, as the reference).
+ *   Z0 (nb, m) lifted initial states; U (T-1, nb, p) controls, step-major; Yhat (T, nb, d) output, may be NULL;
+ *   Ytrue (T, nb, d) optional: if given, sq_err (nb) = sum_{i,j} (Ytrue-Yhat)^2 and sq_sim (nb) = sum Yhat^2
+ *   (the scripts' two RMSE definitions, _cloth.py:34 and _classic.py:39, are formed from these on the host).
+ *   Zfinal (nb, m) optional: lifted state after the last step. */
+int nk_rollout(nk_handle *h, int m, int p, int d, int T, long long nb, const double *A, const double *B, const double *C,
+               const double *Z0, const double *U, double *Yhat, const double *Ytrue, double *sq_err, double *sq_sim,
+               double *Zfinal, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

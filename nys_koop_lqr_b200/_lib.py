@@ -1,0 +1,71 @@
+"""ctypes binding of libnkb200.so (the C ABI declared in include/nk_b200.h).
+
+There is no fallback: if the shared library is missing or no sm_100 GPU is usable, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import pathlib
+
+_HERE = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libnkb200.so"
+
+NK_KERNEL_RBF, NK_KERNEL_MATERN52 = 0, 1
+
+_c_dp = C.c_void_p  # device pointers are passed as integers
+_ll = C.c_longlong
+_i = C.c_int
+_d = C.c_double
+
+_SIGNATURES = {
+    "nk_version": ([], _i),
+    "nk_create": ([C.POINTER(C.c_void_p), _i], _i),
+    "nk_destroy": ([C.c_void_p], _i),
+    "nk_last_error_string": ([C.c_void_p], C.c_char_p),
+    "nk_device_sm_count": ([C.c_void_p], _i),
+    "nk_gram_begin": ([C.c_void_p, _c_dp, _ll, _i, _i, _i, _c_dp, _i, _i, C.c_void_p], _i),
+    "nk_gram_update": ([C.c_void_p, _c_dp, _ll, _c_dp, _ll, _ll, C.c_void_p], _i),
+    "nk_gram_finalize": ([C.c_void_p] + [_c_dp, _ll] * 7 + [_i, C.c_void_p], _i),
+    "nk_gram_last_executed_flops": ([C.c_void_p], _d),
+    "nk_launch_count": ([C.c_void_p], _ll),
+    "nk_kzz": ([C.c_void_p, _c_dp, _ll, _i, _i, _c_dp, _i, _c_dp, _ll, C.c_void_p], _i),
+    "nk_kernel_cross": ([C.c_void_p, _c_dp, _ll, _i, _i, _c_dp, _i, _c_dp, _ll, _ll, _c_dp, _ll, C.c_void_p], _i),
+    "nk_gemm": ([C.c_void_p, _i, _i, _i, _i, _i, _d, _c_dp, _ll, _c_dp, _ll, _d, _c_dp, _ll, C.c_void_p], _i),
+    "nk_potrf": ([C.c_void_p, _i, _c_dp, _ll, C.POINTER(_i), C.c_void_p], _i),
+    "nk_trsm_lower": ([C.c_void_p, _i, _i, _i, _c_dp, _ll, _c_dp, _ll, C.c_void_p], _i),
+    "nk_sym_sqrt": ([C.c_void_p, _i, _c_dp, _ll, _d, _c_dp, _ll, _c_dp, _ll, C.POINTER(_i), C.c_void_p], _i),
+    "nk_solve_abc": ([C.c_void_p, _i, _i, _i, _d, _d] + [_c_dp] * 14 + [C.POINTER(_i), C.c_void_p], _i),
+    "nk_lift": ([C.c_void_p, _c_dp, _ll, _i, _i, _c_dp, _i, _c_dp, _ll, _c_dp, _ll, _ll, _c_dp, _ll, _c_dp, _ll, C.c_void_p], _i),
+    "nk_predict": ([C.c_void_p, _c_dp, _ll, _i, _i, _i, _c_dp, _i, _c_dp, _ll, _c_dp, _ll, _c_dp, _ll, _ll, _c_dp, _ll, C.c_void_p], _i),
+    "nk_rollout": ([C.c_void_p, _i, _i, _i, _i, _ll] + [_c_dp] * 10 + [C.c_void_p], _i),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+class NkError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the in-tree shared library (built by nys_koop_lqr_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise NkError(f"{LIB_PATH} is missing: run `python -m nys_koop_lqr_b200.build` (no CPU fallback exists)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (argtypes, restype) in _SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError here means the .so does not export what include/nk_b200.h declares
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+def check(handle, rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().nk_last_error_string(handle)
+        raise NkError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,225 @@
+// nk_api.cu -- extern "C" entry points of libnkb200.so: handle life-cycle and the fused lift+Gram path.
+// (dense stage: nk_dense.cu; lift/rollout: nk_rollout.cu)
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include "nk_handle.cuh"
+
+namespace nk {
+
+static std::string g_create_err;
+
+int set_err(nk_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg; else g_create_err = msg;
+    return code;
+}
+int check_cuda(nk_handle *h, cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return NK_OK;
+    return set_err(h, NK_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+int ensure(nk_handle *h, nk_devbuf &b, size_t bytes) {
+    if (bytes == 0) bytes = 8;
+    if (b.bytes >= bytes) return NK_OK;
+    if (b.ptr) { cudaFree(b.ptr); b.ptr = nullptr; b.bytes = 0; }
+    cudaError_t e = cudaMalloc(&b.ptr, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(h, NK_E_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e)); }
+    b.bytes = bytes;
+    return NK_OK;
+}
+
+void launch_pack_landmarks(const double *Z, long long ldz, int m, int d, int MP, int KLS, const double *inv_ls,
+                           const double *center, double *ZP, cudaStream_t stream);
+void launch_unpack(const double *Gws, const int *tile_of, int nblk, int row0, int col0, int rows, int cols,
+                   double *out, long long ld, int accumulate, cudaStream_t stream);
+
+// centre = mean of the landmarks: shrinks |x'|^2 + |z'|^2 in the norm expansion (distances are shift invariant)
+__global__ void landmark_center_kernel(const double *Z, long long ldz, int m, int d, double *center) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= d) return;
+    double s = 0.0;
+    for (int r = 0; r < m; r++) s += Z[(long long)r * ldz + k];
+    center[k] = s / m;
+}
+
+}  // namespace nk
+
+using namespace nk;
+
+extern "C" {
+
+int nk_version(void) { return 100; }
+
+int nk_create(nk_handle **out, int device) {
+    if (!out) return set_err(nullptr, NK_E_INVALID, "nk_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return set_err(nullptr, NK_E_CUDA, "nk_create: no CUDA device (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= count) return set_err(nullptr, NK_E_INVALID, "nk_create: bad device index");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return set_err(nullptr, NK_E_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    if (prop.major != 10) return set_err(nullptr, NK_E_CUDA, "nk_create: device is not sm_100 (kernels are built for sm_100a only)");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return set_err(nullptr, NK_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    nk_handle *h = new nk_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    *out = h;
+    return NK_OK;
+}
+
+int nk_destroy(nk_handle *h) {
+    if (!h) return NK_OK;
+    cudaSetDevice(h->device);
+    nk_devbuf *bufs[] = {&h->zp, &h->inv_ls, &h->center, &h->xp[0], &h->xp[1], &h->yp[0], &h->yp[1], &h->psi[0], &h->psi[1],
+                         &h->gws, &h->items, &h->counters, &h->tile_of, &h->dinfo};
+    for (nk_devbuf *b : bufs) if (b->ptr) cudaFree(b->ptr);
+    for (nk_devbuf &b : h->dense) if (b.ptr) cudaFree(b.ptr);
+    delete h;
+    return NK_OK;
+}
+
+const char *nk_last_error_string(nk_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+int nk_device_sm_count(nk_handle *h) { return h ? h->sm_count : 0; }
+double nk_gram_last_executed_flops(nk_handle *h) { return h ? h->last_flops : 0.0; }
+long long nk_launch_count(nk_handle *h) { return h ? h->launches : 0; }
+
+int nk_gram_begin(nk_handle *h, const double *Z, long long ldz, int m, int d, int p, const double *inv_ls, int kind,
+                  int chunk, void *stream_) {
+    if (!h) return NK_E_INVALID;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!Z || !inv_ls || m < 1 || d < 1 || p < 0 || ldz < d) return set_err(h, NK_E_INVALID, "nk_gram_begin: bad argument");
+    if (kind != NK_KERNEL_RBF && kind != NK_KERNEL_MATERN52) return set_err(h, NK_E_INVALID, "nk_gram_begin: unsupported kernel kind");
+    if (p > kTile) return set_err(h, NK_E_INVALID, "nk_gram_begin: more than 128 control inputs are not supported");
+    NK_CUDA(h, cudaSetDevice(h->device));
+    if (chunk <= 0) chunk = 512;
+    chunk = ((chunk + kTile - 1) / kTile) * kTile;
+    h->m = m; h->d = d; h->p = p; h->kind = kind; h->nk_chunk = chunk;
+    h->MP = ((m + kTile - 1) / kTile) * kTile;
+    h->KLS = (d + 2 + kSlabK - 1) / kSlabK;
+    h->EP = ((p + d + kTile - 1) / kTile) * kTile;
+    h->psi_rows = 2 * h->MP + h->EP;
+    const int MB = h->MP / kTile, EB = h->EP / kTile;
+    h->nblk = 2 * MB + EB;
+
+    // ---- accumulator tiles: lower triangle over the feature blocks, plus the [U;Y] products the fit needs ----
+    std::vector<GramItem> sy;
+    h->h_tile_of.assign((size_t)h->nblk * h->nblk, -1);
+    auto add_tile = [&](int I, int J) {
+        const int t = (int)sy.size();
+        h->h_tile_of[(size_t)I * h->nblk + J] = t;
+        sy.push_back(GramItem{kItemSyrk, I, J, t});
+    };
+    for (int I = 0; I < 2 * MB; I++) for (int J = 0; J <= I; J++) add_tile(I, J);
+    const int u_blocks = (p + kTile - 1) / kTile;                 // E blocks holding control rows (0 or 1)
+    for (int e = 0; e < EB; e++) {
+        for (int J = 0; J < 2 * MB; J++) {
+            const bool is_x = J < MB;
+            if (is_x && e >= u_blocks) continue;                  // Y x Phi_x is not needed (regressors.py:164 pairs Y with Phi_y)
+            add_tile(2 * MB + e, J);
+        }
+    }
+    for (int e = 0; e < u_blocks; e++) for (int f = 0; f <= e; f++) add_tile(2 * MB + e, 2 * MB + f);   // U U^T
+    h->ntiles = (int)sy.size();
+    h->n_sy = h->ntiles;
+    h->n_pk = chunk / kTile;
+    h->n_lf = 2 * MB * (chunk / kTile);
+
+    // ---- one period of the global work order: syrk(c) with pack(c+1) at 1/4 and lift(c+1) at 1/2 ----
+    std::vector<GramItem> period;
+    const int q1 = h->n_sy / 4, q2 = h->n_sy / 2;
+    for (int i = 0; i < q1; i++) period.push_back(sy[i]);
+    for (int sb = 0; sb < h->n_pk; sb++) period.push_back(GramItem{kItemPack, sb, 0, 0});
+    for (int i = q1; i < q2; i++) period.push_back(sy[i]);
+    for (int sb = 0; sb < chunk / kTile; sb++)
+        for (int side = 0; side < 2; side++)
+            for (int lb = 0; lb < MB; lb++) period.push_back(GramItem{kItemLift, side, lb, sb});
+    for (int i = q2; i < h->n_sy; i++) period.push_back(sy[i]);
+    h->period_len = (int)period.size();
+
+    int rc;
+    if ((rc = ensure(h, h->zp, (size_t)h->MP * h->KLS * kSlabK * 8)) != NK_OK) return rc;
+    if ((rc = ensure(h, h->inv_ls, (size_t)d * 8)) != NK_OK) return rc;
+    if ((rc = ensure(h, h->center, (size_t)d * 8)) != NK_OK) return rc;
+    for (int s = 0; s < 2; s++) {
+        if ((rc = ensure(h, h->xp[s], (size_t)chunk * h->KLS * kSlabK * 8)) != NK_OK) return rc;
+        if ((rc = ensure(h, h->yp[s], (size_t)chunk * h->KLS * kSlabK * 8)) != NK_OK) return rc;
+        if ((rc = ensure(h, h->psi[s], (size_t)h->psi_rows * chunk * 8)) != NK_OK) return rc;
+    }
+    if ((rc = ensure(h, h->gws, (size_t)h->ntiles * kTile * kTile * 8)) != NK_OK) return rc;
+    if ((rc = ensure(h, h->items, period.size() * sizeof(GramItem))) != NK_OK) return rc;
+    if ((rc = ensure(h, h->counters, (size_t)(kCounterTileVer + h->ntiles) * sizeof(int))) != NK_OK) return rc;
+    if ((rc = ensure(h, h->tile_of, h->h_tile_of.size() * sizeof(int))) != NK_OK) return rc;
+
+    NK_CUDA(h, cudaMemcpyAsync(h->items.ptr, period.data(), period.size() * sizeof(GramItem), cudaMemcpyHostToDevice, stream));
+    NK_CUDA(h, cudaMemcpyAsync(h->tile_of.ptr, h->h_tile_of.data(), h->h_tile_of.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    NK_CUDA(h, cudaStreamSynchronize(stream));   // `period` and h_tile_of staging are host temporaries
+    NK_CUDA(h, cudaMemcpyAsync(h->inv_ls.ptr, inv_ls, (size_t)d * 8, cudaMemcpyDeviceToDevice, stream));
+    landmark_center_kernel<<<(d + 127) / 128, 128, 0, stream>>>(Z, ldz, m, d, (double *)h->center.ptr);
+    launch_pack_landmarks(Z, ldz, m, d, h->MP, h->KLS, (const double *)h->inv_ls.ptr, (const double *)h->center.ptr,
+                          (double *)h->zp.ptr, stream);
+    NK_CUDA(h, cudaMemsetAsync(h->gws.ptr, 0, (size_t)h->ntiles * kTile * kTile * 8, stream));
+    NK_CUDA(h, cudaGetLastError());
+    h->launches += 2;
+    h->gram_open = true;
+    h->last_flops = 0.0;
+    return NK_OK;
+}
+
+int nk_gram_update(nk_handle *h, const double *X, long long ldx, const double *Y, long long ldy, long long n, void *stream_) {
+    if (!h) return NK_E_INVALID;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!h->gram_open) return set_err(h, NK_E_STATE, "nk_gram_update: call nk_gram_begin first");
+    if (n == 0) return NK_OK;
+    if (!X || !Y || n < 0 || ldx < h->d + h->p || ldy < h->d) return set_err(h, NK_E_INVALID, "nk_gram_update: bad argument");
+    NK_CUDA(h, cudaSetDevice(h->device));
+    const long long n_chunks = (n + h->nk_chunk - 1) / h->nk_chunk;
+    if ((n_chunks + 1) * (long long)h->period_len > 2000000000LL || (n_chunks / 2 + 1) * (long long)h->n_sy * kConsumerWarps > 2000000000LL)
+        return set_err(h, NK_E_INVALID, "nk_gram_update: too many chunks for one call; split the sample block");
+    GramParams P;
+    P.X = X; P.ldx = ldx; P.Y = Y; P.ldy = ldy; P.n = n;
+    P.d = h->d; P.p = h->p; P.m = h->m; P.kind = h->kind;
+    P.MP = h->MP; P.KLS = h->KLS; P.nk = h->nk_chunk; P.n_chunks = (int)n_chunks;
+    P.psi_rp = h->psi_rows / kPanel; P.e_row0 = 2 * h->MP; P.EP = h->EP;
+    P.ZP = (const double *)h->zp.ptr; P.inv_ls = (const double *)h->inv_ls.ptr; P.center = (const double *)h->center.ptr;
+    for (int s = 0; s < 2; s++) { P.XP[s] = (double *)h->xp[s].ptr; P.YP[s] = (double *)h->yp[s].ptr; P.PSI[s] = (double *)h->psi[s].ptr; }
+    P.Gws = (double *)h->gws.ptr;
+    P.items = (const GramItem *)h->items.ptr;
+    P.period_len = h->period_len; P.n_pk = h->n_pk; P.n_lf = h->n_lf; P.n_sy = h->n_sy;
+    P.counters = (int *)h->counters.ptr;
+    NK_CUDA(h, cudaMemsetAsync(h->counters.ptr, 0, (size_t)(kCounterTileVer + h->ntiles) * sizeof(int), stream));
+    cudaError_t e = cudaSuccess;
+    launch_gram(P, h->sm_count, stream, &e);
+    NK_CUDA(h, e);
+    h->launches += 1;
+    const double per_tile = 2.0 * kTile * kTile;
+    h->last_flops = (double)n_chunks * ((double)h->n_sy * per_tile * h->nk_chunk + (double)h->n_lf * per_tile * h->KLS * kSlabK);
+    return NK_OK;
+}
+
+int nk_gram_finalize(nk_handle *h, double *Gxx, long long ld_gxx, double *Gyx, long long ld_gyx, double *Gyy, long long ld_gyy,
+                     double *Gxu, long long ld_gxu, double *Gyu, long long ld_gyu, double *Guu, long long ld_guu,
+                     double *GYy, long long ld_gYy, int accumulate, void *stream_) {
+    if (!h) return NK_E_INVALID;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!h->gram_open) return set_err(h, NK_E_STATE, "nk_gram_finalize: call nk_gram_begin first");
+    NK_CUDA(h, cudaSetDevice(h->device));
+    const double *G = (const double *)h->gws.ptr;
+    const int *tof = (const int *)h->tile_of.ptr;
+    const int m = h->m, p = h->p, d = h->d, MP = h->MP, E0 = 2 * h->MP, nb = h->nblk;
+    if (Gxx) { launch_unpack(G, tof, nb, 0, 0, m, m, Gxx, ld_gxx, accumulate, stream); h->launches++; }
+    if (Gyx) { launch_unpack(G, tof, nb, MP, 0, m, m, Gyx, ld_gyx, accumulate, stream); h->launches++; }
+    if (Gyy) { launch_unpack(G, tof, nb, MP, MP, m, m, Gyy, ld_gyy, accumulate, stream); h->launches++; }
+    if (Gxu && p) { launch_unpack(G, tof, nb, 0, E0, m, p, Gxu, ld_gxu, accumulate, stream); h->launches++; }
+    if (Gyu && p) { launch_unpack(G, tof, nb, MP, E0, m, p, Gyu, ld_gyu, accumulate, stream); h->launches++; }
+    if (Guu && p) { launch_unpack(G, tof, nb, E0, E0, p, p, Guu, ld_guu, accumulate, stream); h->launches++; }
+    if (GYy) { launch_unpack(G, tof, nb, E0 + p, MP, d, m, GYy, ld_gYy, accumulate, stream); h->launches++; }
+    NK_CUDA(h, cudaGetLastError());
+    return NK_OK;
+}
+
+}  // extern "C"

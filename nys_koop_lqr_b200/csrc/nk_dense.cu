@@ -1,0 +1,665 @@
+// nk_dense.cu -- the n-independent dense FP64 stage on DMMA: GEMM, blocked Cholesky, triangular solves,
+// symmetric square root, and the Grams -> (A, B, C, W) solve of regressors.py:139-140,147-169.
+//
+// Everything is phrased as "NT" products  C = A B^T  with both operands contraction-contiguous, so one staging
+// path (16-byte cp.async into the 8x8-block shared layout of nk_common.cuh) feeds the same 64x32 DMMA warp tile
+// as the fused Gram engine.  Triangular solves keep the unknown TRANSPOSED (X^T rows = right-hand sides), which
+// turns every block update of forward/backward substitution into an NT product; 128x128 diagonal blocks are
+// factored and inverted by a single-CTA kernel.
+//
+// Symmetric square root (scipy.linalg.sqrtm at regressors.py:140,163,175): K = L L^T, polar decomposition
+// L^T = Q H by Newton-Schulz with the minimax cubic on [l,1] (l tracked analytically from the eigenvalue bound),
+// S = H = Q^T L^T, S^-1 = L^-T Q.  Measured against eigh / sqrtm in tools/proto/polar_sqrt.py: same floor.
+#include <cmath>
+#include <cstdio>
+#include <vector>
+#include "nk_dense.cuh"
+
+namespace nk {
+
+constexpr int kGemmStages = 4;
+constexpr size_t kGemmSmem = (size_t)kGemmStages * 2 * kSlabTileDoubles * 8;
+
+struct GemmArgs {
+    int M, N, K;
+    double alpha, beta, diag;
+    const double *A; long long lda;
+    const double *B; long long ldb;
+    double *C; long long ldc;
+    double *Ct; long long ldct;
+    int flags, epi_kind, tiles_n;
+};
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src, int bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// stage one 128 x 16 operand slab (rows row0.., depth k0..) into the 8x8-block layout
+template <int VEC>
+__device__ __forceinline__ void stage_slab(double *dst, const double *src, long long ld, int row0, int nrows, int k0, int K, int tid) {
+    if (VEC == 2) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int idx = tid + e * 256;
+            const int row = idx >> 3, kk = (idx & 7) * 2;
+            const int gr = row0 + row, gk = k0 + kk;
+            int bytes = 0;
+            const double *s = src;
+            if (gr < nrows && gk < K) { bytes = (K - gk >= 2) ? 16 : 8; s = src + (long long)gr * ld + gk; }
+            cp_async16(dst + ((row >> 3) * 2 + (kk >> 3)) * kBlk + (row & 7) * 8 + (kk & 7), s, bytes);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int idx = tid + e * 256;
+            const int row = idx >> 4, kk = idx & 15;
+            const int gr = row0 + row, gk = k0 + kk;
+            int bytes = 0;
+            const double *s = src;
+            if (gr < nrows && gk < K) { bytes = 8; s = src + (long long)gr * ld + gk; }
+            cp_async8(dst + ((row >> 3) * 2 + (kk >> 3)) * kBlk + (row & 7) * 8 + (kk & 7), s, bytes);
+        }
+    }
+}
+
+__device__ __forceinline__ void warp_mma_slab_d(double (&acc)[8][4][2], const double *As, const double *Bs, int wr, int wc, int lane) {
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        double2 a[8], b[4];
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = *reinterpret_cast<const double2 *>(As + ((wr * 8 + i) * 2 + q) * kBlk + lane * 2);
+#pragma unroll
+        for (int j = 0; j < 4; j++) b[j] = *reinterpret_cast<const double2 *>(Bs + ((wc * 4 + j) * 2 + q) * kBlk + lane * 2);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256, 1) gemm_nt_kernel(const GemmArgs g) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    double *sm = reinterpret_cast<double *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int I, J;
+    if (g.flags & kGemmLowerOnly) {
+        // blockIdx.x enumerates the lower triangle row by row
+        const int t = blockIdx.x;
+        int r = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+        while ((r + 1) * (r + 2) / 2 <= t) r++;
+        while (r * (r + 1) / 2 > t) r--;
+        I = r; J = t - r * (r + 1) / 2;
+    } else {
+        I = blockIdx.x / g.tiles_n; J = blockIdx.x % g.tiles_n;
+    }
+    const int nslabs = (g.K + kSlabK - 1) / kSlabK;
+    const int wr = warp >> 2, wc = warp & 3;
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+#pragma unroll
+    for (int s = 0; s < kGemmStages - 1; s++) {
+        if (s < nslabs) {
+            double *st = sm + (size_t)s * 2 * kSlabTileDoubles;
+            stage_slab<VEC>(st, g.A, g.lda, I * kTile, g.M, s * kSlabK, g.K, tid);
+            stage_slab<VEC>(st + kSlabTileDoubles, g.B, g.ldb, J * kTile, g.N, s * kSlabK, g.K, tid);
+        }
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nslabs; kt++) {
+        cp_async_wait<kGemmStages - 2>();
+        __syncthreads();
+        const int nxt = kt + kGemmStages - 1;
+        if (nxt < nslabs) {
+            double *st = sm + (size_t)(nxt % kGemmStages) * 2 * kSlabTileDoubles;
+            stage_slab<VEC>(st, g.A, g.lda, I * kTile, g.M, nxt * kSlabK, g.K, tid);
+            stage_slab<VEC>(st + kSlabTileDoubles, g.B, g.ldb, J * kTile, g.N, nxt * kSlabK, g.K, tid);
+        }
+        cp_async_commit();
+        const double *st = sm + (size_t)(kt % kGemmStages) * 2 * kSlabTileDoubles;
+        warp_mma_slab_d(acc, st, st + kSlabTileDoubles, wr, wc, lane);
+    }
+    cp_async_wait<0>();
+
+    const int gq = lane >> 2, t = lane & 3;
+    const bool mirror = (g.flags & kGemmMirror) != 0;   // symmetric result: element (r,c), r >= c, is also written to (c,r)
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int r = I * kTile + wr * 64 + i * 8 + gq;
+        if (r >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int c = J * kTile + wc * 32 + j * 8 + 2 * t + e;
+                if (c >= g.N) continue;
+                if (mirror && c > r) continue;   // diagonal tile: keep one accumulation per symmetric pair
+                double v;
+                if (g.epi_kind >= 0) {
+                    v = kernel_from_exponent(acc[i][j][e], g.epi_kind);
+                    if ((g.flags & kGemmUnitDiag) && r == c) v = 1.0;
+                } else {
+                    v = g.alpha * acc[i][j][e];
+                    if (g.beta != 0.0) v += g.beta * g.C[(long long)r * g.ldc + c];
+                    if (r == c) v += g.diag;
+                }
+                if (g.C) g.C[(long long)r * g.ldc + c] = v;
+                if (mirror && c != r) g.C[(long long)c * g.ldc + r] = v;
+                if (g.flags & kGemmStoreT) g.Ct[(long long)c * g.ldct + r] = v;
+            }
+        }
+    }
+}
+
+void gemm_nt(nk_handle *h, int M, int N, int K, double alpha, const double *A, long long lda, const double *B, long long ldb,
+             double beta, double *C, long long ldc, double diag, int flags, double *Ct, long long ldct, cudaStream_t stream,
+             int epi_kind) {
+    if (M <= 0 || N <= 0) return;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
+        cudaFuncSetAttribute(gemm_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
+        configured = true;
+    }
+    GemmArgs g;
+    g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.diag = diag;
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc; g.Ct = Ct; g.ldct = ldct;
+    g.flags = flags; g.epi_kind = epi_kind;
+    const int tm = (M + kTile - 1) / kTile, tn = (N + kTile - 1) / kTile;
+    g.tiles_n = tn;
+    const int grid = (flags & kGemmLowerOnly) ? tm * (tm + 1) / 2 : tm * tn;
+    const bool vec2 = ((lda | ldb) % 2 == 0) && (((uintptr_t)A | (uintptr_t)B) % 16 == 0);
+    if (vec2) gemm_nt_kernel<2><<<grid, 256, kGemmSmem, stream>>>(g);
+    else gemm_nt_kernel<1><<<grid, 256, kGemmSmem, stream>>>(g);
+    h->launches++;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------------
+__global__ void transpose_kernel(int rows, int cols, const double *src, long long lds, double *dst, long long ldd) {
+    __shared__ double tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int r = by + j, c = bx + threadIdx.x;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = src[(long long)r * lds + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c = bx + j, r = by + threadIdx.x;
+        if (r < rows && c < cols) dst[(long long)c * ldd + r] = tile[threadIdx.x][j];
+    }
+}
+void transpose(nk_handle *h, int rows, int cols, const double *src, long long lds, double *dst, long long ldd, cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0) return;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    transpose_kernel<<<grid, block, 0, stream>>>(rows, cols, src, lds, dst, ldd);
+    h->launches++;
+}
+
+// out = 0.5 (in + in^T)
+__global__ void symmetrize_kernel(int n, const double *in, long long ldi, double *out, long long ldo) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c < n) out[(long long)r * ldo + c] = 0.5 * (in[(long long)r * ldi + c] + in[(long long)c * ldi + r]);
+}
+// dst = scale * src (rows x cols)
+__global__ void scale_copy_kernel(int rows, int cols, double scale, const double *src, long long lds, double *dst, long long ldd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c < cols) dst[(long long)r * ldd + c] = scale * src[(long long)r * lds + c];
+}
+__global__ void zero_upper_kernel(int n, double *A, long long lda) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c < n && c > r) A[(long long)r * lda + c] = 0.0;
+}
+__global__ void rowsum_max_kernel(int n, const double *A, long long lda, double *out) {
+    // out[0] = max_r sum_c |A(r,c)|   (out must be zeroed; doubles are non-negative so the int64 compare order is monotone)
+    const int r = blockIdx.x;
+    double s = 0.0;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) s += fabs(A[(long long)r * lda + c]);
+    __shared__ double red[256];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long *>(out), (unsigned long long)__double_as_longlong(red[0]));
+}
+static void launch2d(int rows, int cols, dim3 &grid, dim3 &block) { block = dim3(128); grid = dim3((cols + 127) / 128, rows); }
+
+__global__ void landmark_center_kernel2(const double *Z, long long ldz, int m, int d, double *center) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= d) return;
+    double s = 0.0;
+    for (int r = 0; r < m; r++) s += Z[(long long)r * ldz + k];
+    center[k] = s / m;
+}
+void landmark_center(const double *Z, long long ldz, int m, int d, double *center, cudaStream_t stream) {
+    landmark_center_kernel2<<<(d + 127) / 128, 128, 0, stream>>>(Z, ldz, m, d, center);
+}
+
+__global__ void augment_rows_kernel(const double *src, long long lds, long long rows, int d, const double *inv_ls, const double *center,
+                                    int landmark_form, double *out, int KA) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    double nrm = 0.0;
+    for (int k = lane; k < KA; k += 32) {
+        double v = 0.0;
+        if (k < d) { v = (src[row * lds + k] - center[k]) * inv_ls[k]; nrm += v * v; }
+        if (k < d || k >= d + 2) out[row * KA + k] = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    if (lane == 0) {
+        out[row * KA + d] = landmark_form ? 1.0 : -0.5 * nrm;
+        out[row * KA + d + 1] = landmark_form ? -0.5 * nrm : 1.0;
+    }
+}
+void augment_rows(nk_handle *h, const double *src, long long lds, long long rows, int d, const double *inv_ls, const double *center,
+                  int landmark_form, double *out, int KA, cudaStream_t stream) {
+    if (rows <= 0) return;
+    const int warps = 8;
+    augment_rows_kernel<<<(unsigned)((rows + warps - 1) / warps), warps * 32, 0, stream>>>(src, lds, rows, d, inv_ls, center, landmark_form, out, KA);
+    h->launches++;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 128 x 128 diagonal block: Cholesky + inverse of the factor, one CTA
+// ---------------------------------------------------------------------------------------------------
+constexpr int kDB = 128, kDBld = 129;
+__global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double *A, long long lda, int nb, int j0, double *dinv, double *dinvT, int *info, int do_factor) {
+    extern __shared__ double Ls[];   // kDB x kDBld
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < kDB * kDB; idx += 256) {
+        const int r = idx / kDB, c = idx % kDB;
+        double v = (r == c) ? 1.0 : 0.0;
+        if (r < nb && c < nb) v = (c <= r) ? A[(long long)r * lda + c] : 0.0;
+        Ls[r * kDBld + c] = v;
+    }
+    __syncthreads();
+    // right-looking Cholesky on the lower triangle (skipped when the block already holds a factor)
+    for (int k = 0; k < (do_factor ? nb : 0); k++) {
+        const double akk = Ls[k * kDBld + k];
+        double piv;
+        if (!(akk > 0.0)) { piv = 1.0; if (tid == 0) atomicCAS(info, 0, j0 + k + 1); }
+        else piv = sqrt(akk);
+        __syncthreads();
+        if (tid == 0) Ls[k * kDBld + k] = piv;
+        for (int i = k + 1 + tid; i < nb; i += 256) Ls[i * kDBld + k] /= piv;
+        __syncthreads();
+        // trailing update of rows i > k, columns k < j <= i
+        const int rem = nb - k - 1;
+        for (int idx = tid; idx < rem * rem; idx += 256) {
+            const int i = k + 1 + idx / rem, j = k + 1 + idx % rem;
+            if (j <= i) Ls[i * kDBld + j] -= Ls[i * kDBld + k] * Ls[j * kDBld + k];
+        }
+        __syncthreads();
+    }
+    // write L (and zero the strict upper part of the block)
+    for (int idx = tid; idx < (do_factor ? nb * nb : 0); idx += 256) {
+        const int r = idx / nb, c = idx % nb;
+        A[(long long)r * lda + c] = (c <= r) ? Ls[r * kDBld + c] : 0.0;
+    }
+    __syncthreads();
+    // inverse: thread j solves L x = e_j; x_i (i > j) is parked in the unused upper triangle at Ls[j][i]
+    if (tid < kDB) {
+        const int j = tid;
+        const double xjj = 1.0 / Ls[j * kDBld + j];
+        for (int i = j + 1; i < kDB; i++) {
+            double s0 = Ls[i * kDBld + j] * xjj, s1 = 0.0;
+            int k = j + 1;
+            for (; k + 1 < i; k += 2) {
+                s0 += Ls[i * kDBld + k] * Ls[j * kDBld + k];
+                s1 += Ls[i * kDBld + k + 1] * Ls[j * kDBld + k + 1];
+            }
+            if (k < i) s0 += Ls[i * kDBld + k] * Ls[j * kDBld + k];
+            Ls[j * kDBld + i] = -(s0 + s1) / Ls[i * kDBld + i];
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < kDB * kDB; idx += 256) {
+        const int r = idx / kDB, c = idx % kDB;   // Linv(r,c), r >= c
+        double v = 0.0;
+        if (c < r) v = Ls[c * kDBld + r];
+        else if (c == r) v = 1.0 / Ls[r * kDBld + r];
+        dinv[idx] = v;
+        dinvT[c * kDB + r] = v;
+    }
+}
+
+int potrf_blocked(nk_handle *h, int n, double *A, long long lda, double *Lt, long long ldlt, double *dinv, double *dinvT,
+                  int *dinfo, cudaStream_t stream) {
+    static bool configured = false;
+    const size_t smem = (size_t)kDB * kDBld * 8;
+    if (!configured) { cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+    cudaMemsetAsync(dinfo, 0, sizeof(int), stream);
+    const int nblk = (n + kDB - 1) / kDB;
+    for (int kb = 0; kb < nblk; kb++) {
+        const int j0 = kb * kDB, nb = (n - j0 < kDB) ? n - j0 : kDB, rem = n - j0 - nb;
+        double *Akk = A + (long long)j0 * lda + j0;
+        double *di = dinv + (size_t)kb * kDB * kDB;
+        potrf_diag_kernel<<<1, 256, smem, stream>>>(Akk, lda, nb, j0, di, dinvT + (size_t)kb * kDB * kDB, dinfo, 1);
+        h->launches++;
+        if (rem > 0) {
+            double *A21 = A + (long long)(j0 + nb) * lda + j0;
+            gemm_nt(h, rem, nb, nb, 1.0, A21, lda, di, kDB, 0.0, A21, lda, 0.0, 0, nullptr, 0, stream);
+            double *A22 = A + (long long)(j0 + nb) * lda + (j0 + nb);
+            gemm_nt(h, rem, rem, nb, -1.0, A21, lda, A21, lda, 1.0, A22, lda, 0.0, kGemmLowerOnly, nullptr, 0, stream);
+        }
+    }
+    dim3 grid, block;
+    launch2d(n, n, grid, block);
+    zero_upper_kernel<<<grid, block, 0, stream>>>(n, A, lda);
+    h->launches++;
+    if (Lt) transpose(h, n, n, A, lda, Lt, ldlt, stream);
+    return NK_OK;
+}
+
+void trsm_fwd_t(nk_handle *h, int n, int r, const double *L, long long ldl, const double *dinv, double *Xt, long long ldx, cudaStream_t stream) {
+    const int nblk = (n + kDB - 1) / kDB;
+    for (int i = 0; i < nblk; i++) {
+        const int j0 = i * kDB, nb = (n - j0 < kDB) ? n - j0 : kDB;
+        if (i > 0) gemm_nt(h, r, nb, j0, -1.0, Xt, ldx, L + (long long)j0 * ldl, ldl, 1.0, Xt + j0, ldx, 0.0, 0, nullptr, 0, stream);
+        gemm_nt(h, r, nb, nb, 1.0, Xt + j0, ldx, dinv + (size_t)i * kDB * kDB, kDB, 0.0, Xt + j0, ldx, 0.0, 0, nullptr, 0, stream);
+    }
+}
+void trsm_bwd_t(nk_handle *h, int n, int r, const double *Lt, long long ldlt, const double *dinvT, double *Xt, long long ldx, cudaStream_t stream) {
+    const int nblk = (n + kDB - 1) / kDB;
+    for (int i = nblk - 1; i >= 0; i--) {
+        const int j0 = i * kDB, nb = (n - j0 < kDB) ? n - j0 : kDB, j1 = j0 + nb;
+        if (j1 < n) gemm_nt(h, r, nb, n - j1, -1.0, Xt + j1, ldx, Lt + (long long)j0 * ldlt + j1, ldlt, 1.0, Xt + j0, ldx, 0.0, 0, nullptr, 0, stream);
+        gemm_nt(h, r, nb, nb, 1.0, Xt + j0, ldx, dinvT + (size_t)i * kDB * kDB, kDB, 0.0, Xt + j0, ldx, 0.0, 0, nullptr, 0, stream);
+    }
+}
+
+double *dense_scratch(nk_handle *h, int slot, size_t doubles, int *rc) {
+    *rc = ensure(h, h->dense[slot], doubles * 8);
+    return (double *)h->dense[slot].ptr;
+}
+
+// minimax odd cubic p(x) = a x - b x^3 on [l, 1], rescaled so that max p = 1; returns the new lower bound
+static double opt_cubic(double l, double *a, double *b) {
+    const double s = 1.0 + l + l * l, xs = std::sqrt(s / 3.0);
+    double bb = 2.0 / ((2.0 * s / 3.0) * xs + (l + l * l));
+    double aa = bb * s;
+    const double pmax = (2.0 * aa / 3.0) * xs, pmin = aa - bb;
+    *a = aa / pmax; *b = bb / pmax;
+    return pmin / pmax;
+}
+
+static inline int even(int x) { return (x + 1) & ~1; }
+
+}  // namespace nk
+
+using namespace nk;
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+int nk_gemm(nk_handle *h, int transa, int transb, int M, int N, int K, double alpha, const double *A, long long lda,
+            const double *B, long long ldb, double beta, double *C, long long ldc, void *stream_) {
+    if (!h) return NK_E_INVALID;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (M < 0 || N < 0 || K < 0 || !A || !B || !C) return set_err(h, NK_E_INVALID, "nk_gemm: bad argument");
+    NK_CUDA(h, cudaSetDevice(h->device));
+    int rc = NK_OK;
+    const double *Ak = A; long long ldak = lda;      // (M,K) k-contiguous
+    const double *Bk = B; long long ldbk = ldb;      // (N,K) k-contiguous
+    if (transa) {  // stored (K,M): transpose into scratch
+        double *t = dense_scratch(h, 10, (size_t)M * even(K), &rc); if (rc) return rc;
+        transpose(h, K, M, A, lda, t, even(K), stream); Ak = t; ldak = even(K);
+    }
+    if (!transb) { // stored (K,N): transpose into scratch
+        double *t = dense_scratch(h, 11, (size_t)N * even(K), &rc); if (rc) return rc;
+        transpose(h, K, N, B, ldb, t, even(K), stream); Bk = t; ldbk = even(K);
+    }
+    gemm_nt(h, M, N, K, alpha, Ak, ldak, Bk, ldbk, beta, C, ldc, 0.0, 0, nullptr, 0, stream);
+    NK_CUDA(h, cudaGetLastError());
+    return NK_OK;
+}
+
+int nk_potrf(nk_handle *h, int n, double *A, long long lda, int *info, void *stream_) {
+    if (!h) return NK_E_INVALID;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 1 || !A || lda < n) return set_err(h, NK_E_INVALID, "nk_potrf: bad argument");
+    NK_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    const int nblk = (n + kDB - 1) / kDB;
+    double *dinv = dense_scratch(h, 8, (size_t)nblk * kDB * kDB, &rc); if (rc) return rc;
+    double *dinvT = dense_scratch(h, 9, (size_t)nblk * kDB * kDB, &rc); if (rc) return rc;
+    if ((rc = ensure(h, h->dinfo, 64)) != NK_OK) return rc;
+    potrf_blocked(h, n, A, lda, nullptr, 0, dinv, dinvT, (int *)h->dinfo.ptr, stream);
+    int hinfo = 0;
+    NK_CUDA(h, cudaMemcpyAsync(&hinfo, h->dinfo.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    NK_CUDA(h, cudaStreamSynchronize(stream));
+    if (info) *info = hinfo;
+    if (hinfo != 0) return set_err(h, NK_E_NOT_SPD, "nk_potrf: matrix is not positive definite (pivot " + std::to_string(hinfo) + ")");
+    return NK_OK;
+}
+
+int nk_trsm_lower(nk_handle *h, int trans, int n, int nrhs, const double *L, long long ldl, double *B, long long ldb, void *stream_) {
+    if (!h) return NK_E_INVALID;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 1 || nrhs < 1 || !L || !B) return set_err(h, NK_E_INVALID, "nk_trsm_lower: bad argument");
+    NK_CUDA(h, cudaSetDevice(h->device));
+    // generic entry: rebuilds the diagonal-block inverses from L (the fused paths reuse the ones potrf produced)
+    int rc;
+    const int nblk = (n + kDB - 1) / kDB, ldn = even(n);
+    double *Lc = dense_scratch(h, 6, (size_t)n * ldn, &rc); if (rc) return rc;
+    double *Lt = dense_scratch(h, 7, (size_t)n * ldn, &rc); if (rc) return rc;
+    double *dinv = dense_scratch(h, 8, (size_t)nblk * kDB * kDB, &rc); if (rc) return rc;
+    double *dinvT = dense_scratch(h, 9, (size_t)nblk * kDB * kDB, &rc); if (rc) return rc;
+    double *Xt = dense_scratch(h, 10, (size_t)nrhs * ldn, &rc); if (rc) return rc;
+    if ((rc = ensure(h, h->dinfo, 64)) != NK_OK) return rc;
+    NK_CUDA(h, cudaMemcpy2DAsync(Lc, ldn * 8, L, ldl * 8, (size_t)n * 8, n, cudaMemcpyDeviceToDevice, stream));
+    // diagonal-block inverses straight from the given factor (do_factor = 0)
+    const size_t smem = (size_t)kDB * kDBld * 8;
+    cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int i = 0; i < nblk; i++) {
+        const int j0 = i * kDB, nb = (n - j0 < kDB) ? n - j0 : kDB;
+        potrf_diag_kernel<<<1, 256, smem, stream>>>(Lc + (long long)j0 * ldn + j0, ldn, nb, j0, dinv + (size_t)i * kDB * kDB,
+                                                    dinvT + (size_t)i * kDB * kDB, (int *)h->dinfo.ptr, 0);
+        h->launches++;
+    }
+    dim3 grid, block; launch2d(n, n, grid, block);
+    zero_upper_kernel<<<grid, block, 0, stream>>>(n, Lc, ldn);
+    transpose(h, n, n, Lc, ldn, Lt, ldn, stream);
+    transpose(h, n, nrhs, B, ldb, Xt, ldn, stream);
+    if (!trans) trsm_fwd_t(h, n, nrhs, Lc, ldn, dinv, Xt, ldn, stream);
+    else trsm_bwd_t(h, n, nrhs, Lt, ldn, dinvT, Xt, ldn, stream);
+    transpose(h, nrhs, n, Xt, ldn, B, ldb, stream);
+    NK_CUDA(h, cudaGetLastError());
+    return NK_OK;
+}
+
+int nk_sym_sqrt(nk_handle *h, int n, const double *K, long long ldk, double lambda_min_bound, double *S, long long lds,
+                double *Sinv, long long ldsi, int *iters, void *stream_) {
+    if (!h) return NK_E_INVALID;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 1 || !K || !S || !Sinv || !(lambda_min_bound > 0.0)) return set_err(h, NK_E_INVALID, "nk_sym_sqrt: bad argument");
+    NK_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    const int ldn = even(n), nblk = (n + kDB - 1) / kDB;
+    const size_t nn = (size_t)n * ldn;
+    double *L = dense_scratch(h, 0, nn, &rc); if (rc) return rc;
+    double *Lt = dense_scratch(h, 1, nn, &rc); if (rc) return rc;
+    double *X = dense_scratch(h, 2, nn, &rc); if (rc) return rc;
+    double *Xt = dense_scratch(h, 3, nn, &rc); if (rc) return rc;
+    double *X2 = dense_scratch(h, 4, nn, &rc); if (rc) return rc;
+    double *Xt2 = dense_scratch(h, 5, nn, &rc); if (rc) return rc;
+    double *T = dense_scratch(h, 6, nn, &rc); if (rc) return rc;
+    double *dinv = dense_scratch(h, 8, (size_t)nblk * kDB * kDB, &rc); if (rc) return rc;
+    double *dinvT = dense_scratch(h, 9, (size_t)nblk * kDB * kDB, &rc); if (rc) return rc;
+    if ((rc = ensure(h, h->dinfo, 64)) != NK_OK) return rc;
+    int *dinfo = (int *)h->dinfo.ptr;
+    double *dnorm = (double *)((char *)h->dinfo.ptr + 16);
+
+    NK_CUDA(h, cudaMemcpy2DAsync(L, ldn * 8, K, ldk * 8, (size_t)n * 8, n, cudaMemcpyDeviceToDevice, stream));
+    NK_CUDA(h, cudaMemsetAsync(dnorm, 0, 8, stream));
+    rowsum_max_kernel<<<n, 256, 0, stream>>>(n, L, ldn, dnorm);
+    potrf_blocked(h, n, L, ldn, Lt, ldn, dinv, dinvT, dinfo, stream);
+    struct { int info; int pad[3]; double nrm2; } host;
+    NK_CUDA(h, cudaMemcpyAsync(&host, h->dinfo.ptr, 24, cudaMemcpyDeviceToHost, stream));
+    NK_CUDA(h, cudaStreamSynchronize(stream));
+    if (host.info != 0) return set_err(h, NK_E_NOT_SPD, "nk_sym_sqrt: matrix is not positive definite (pivot " + std::to_string(host.info) + ")");
+    const double nrm = std::sqrt(host.nrm2);   // >= ||L^T||_2
+    dim3 grid, block; launch2d(n, n, grid, block);
+    scale_copy_kernel<<<grid, block, 0, stream>>>(n, n, 1.0 / nrm, Lt, ldn, X, ldn);
+    scale_copy_kernel<<<grid, block, 0, stream>>>(n, n, 1.0 / nrm, L, ldn, Xt, ldn);
+    h->launches += 3;
+
+    // Newton-Schulz polar iteration  X <- (a I - b X X^T) X  with the minimax cubic while the singular-value lower
+    // bound l < 1, then plain (1.5, 0.5) steps (quadratic convergence) until l reaches 1 to rounding.
+    double l = 0.9 * std::sqrt(lambda_min_bound) / nrm;
+    if (l > 1.0) l = 1.0;
+    int it = 0, plain = 0;
+    while (it < 100) {
+        double a, b;
+        if (l < 0.999) l = opt_cubic(l, &a, &b);
+        else { a = 1.5; b = 0.5; plain++; }
+        gemm_nt(h, n, n, n, -b, X, ldn, X, ldn, 0.0, T, ldn, a, kGemmLowerOnly | kGemmMirror, nullptr, 0, stream);
+        gemm_nt(h, n, n, n, 1.0, T, ldn, Xt, ldn, 0.0, X2, ldn, 0.0, kGemmStoreT, Xt2, ldn, stream);
+        std::swap(X, X2); std::swap(Xt, Xt2);
+        it++;
+        if (plain >= 3) break;
+    }
+    if (iters) *iters = it;
+    // S = Q^T L^T  ->  S(i,j) = sum_k Xt(i,k) L(j,k); symmetrised
+    gemm_nt(h, n, n, n, 1.0, Xt, ldn, L, ldn, 0.0, T, ldn, 0.0, 0, nullptr, 0, stream);
+    symmetrize_kernel<<<grid, block, 0, stream>>>(n, T, ldn, S, lds);
+    // S^-1 = L^-T Q  ->  (S^-1)^T = Q^T L^-1 : backward substitution in transposed storage
+    trsm_bwd_t(h, n, n, Lt, ldn, dinvT, Xt, ldn, stream);
+    symmetrize_kernel<<<grid, block, 0, stream>>>(n, Xt, ldn, Sinv, ldsi);
+    h->launches += 2;
+    NK_CUDA(h, cudaGetLastError());
+    return NK_OK;
+}
+
+// ---- assemble kernels for the two regularised systems ----
+__global__ void assemble_inner_kernel(int m, int p, double gn, double jitter, const double *Gxx, const double *Gxu, const double *Guu,
+                                      const double *Kzz, double *inner, long long ld) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    const int N1 = m + p;
+    if (c >= N1) return;
+    double v;
+    if (r < m && c < m) v = Gxx[(long long)r * m + c] + gn * (Kzz[(long long)r * m + c] + (r == c ? jitter : 0.0));
+    else if (r < m) v = Gxu[(long long)r * p + (c - m)];
+    else if (c < m) v = Gxu[(long long)c * p + (r - m)];
+    else v = Guu[(long long)(r - m) * p + (c - m)] + (r == c ? gn : 0.0);
+    inner[(long long)r * ld + c] = v;
+}
+__global__ void assemble_rec_kernel(int m, double gn, double jitter, const double *Gyy, const double *Kzz, double *out, long long ld) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c >= m) return;
+    out[(long long)r * ld + c] = gn * (Kzz[(long long)r * m + c] + (r == c ? jitter : 0.0)) + Gyy[(long long)r * m + c];
+}
+__global__ void set_identity_block_kernel(int p, double *M, long long ld) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p) M[(long long)i * ld + i] = 1.0;
+}
+
+int nk_solve_abc(nk_handle *h, int m, int p, int d, double gamma_n, double jitter, const double *Gxx, const double *Gyx,
+                 const double *Gyy, const double *Gxu, const double *Gyu, const double *Guu, const double *GYy, const double *Kzz,
+                 const double *S, const double *Sinv, double *A, double *B, double *C, double *W, int *info, void *stream_) {
+    if (!h) return NK_E_INVALID;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (m < 1 || p < 0 || d < 1 || !Gxx || !Gyx || !Gyy || !GYy || !Kzz || !S || !Sinv || !A || !C || !W || (p && (!Gxu || !Gyu || !Guu || !B)))
+        return set_err(h, NK_E_INVALID, "nk_solve_abc: bad argument");
+    NK_CUDA(h, cudaSetDevice(h->device));
+    if (info) *info = 0;
+    int rc;
+    const int N1 = m + p, ld1 = even(N1), ldm = even(m), nblk1 = (N1 + kDB - 1) / kDB;
+    double *inner = dense_scratch(h, 0, (size_t)N1 * ld1, &rc); if (rc) return rc;
+    double *Lt = dense_scratch(h, 1, (size_t)N1 * ld1, &rc); if (rc) return rc;
+    double *Rt = dense_scratch(h, 2, (size_t)N1 * ld1, &rc); if (rc) return rc;
+    double *crossT = dense_scratch(h, 3, (size_t)N1 * ldm, &rc); if (rc) return rc;
+    double *left = dense_scratch(h, 4, (size_t)m * ld1, &rc); if (rc) return rc;
+    double *Gm = dense_scratch(h, 5, (size_t)m * ld1, &rc); if (rc) return rc;
+    double *Gt = dense_scratch(h, 6, (size_t)N1 * ldm, &rc); if (rc) return rc;
+    double *dinv = dense_scratch(h, 8, (size_t)nblk1 * kDB * kDB, &rc); if (rc) return rc;
+    double *dinvT = dense_scratch(h, 9, (size_t)nblk1 * kDB * kDB, &rc); if (rc) return rc;
+    if ((rc = ensure(h, h->dinfo, 64)) != NK_OK) return rc;
+    int *dinfo = (int *)h->dinfo.ptr;
+    dim3 grid, block;
+
+    // ---- dynamics: G = S^-1 [Gyx|Gyu] inner^-1 blkdiag(Kzz S^-1, I)   (regressors.py:147-159) ----
+    launch2d(N1, N1, grid, block);
+    assemble_inner_kernel<<<grid, block, 0, stream>>>(m, p, gamma_n, jitter, Gxx, Gxu, Guu, Kzz, inner, ld1);
+    h->launches++;
+    potrf_blocked(h, N1, inner, ld1, Lt, ld1, dinv, dinvT, dinfo, stream);
+    int hinfo = 0;
+    NK_CUDA(h, cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    NK_CUDA(h, cudaStreamSynchronize(stream));
+    if (hinfo != 0) { if (info) *info = 1; return set_err(h, NK_E_NOT_SPD, "nk_solve_abc: inner_term is not positive definite (pivot " + std::to_string(hinfo) + ")"); }
+    NK_CUDA(h, cudaMemsetAsync(Rt, 0, (size_t)N1 * ld1 * 8, stream));
+    gemm_nt(h, m, m, m, 1.0, Sinv, m, Kzz, m, 0.0, Rt, ld1, 0.0, 0, nullptr, 0, stream);       // right^T = blkdiag(S^-1 Kzz, I)
+    if (p) { set_identity_block_kernel<<<(p + 127) / 128, 128, 0, stream>>>(p, Rt + (long long)m * ld1 + m, ld1); h->launches++; }
+    trsm_fwd_t(h, N1, N1, inner, ld1, dinv, Rt, ld1, stream);                                   // sol^T = right^T inner^-1
+    trsm_bwd_t(h, N1, N1, Lt, ld1, dinvT, Rt, ld1, stream);
+    transpose(h, m, m, Gyx, m, crossT, ldm, stream);                                            // cross^T = [Gyx | Gyu]^T
+    if (p) transpose(h, m, p, Gyu, p, crossT + (long long)m * ldm, ldm, stream);
+    gemm_nt(h, m, N1, m, 1.0, Sinv, m, crossT, ldm, 0.0, left, ld1, 0.0, 0, nullptr, 0, stream);   // left = S^-1 cross
+    gemm_nt(h, m, N1, N1, 1.0, left, ld1, Rt, ld1, 0.0, Gm, ld1, 0.0, kGemmStoreT, Gt, ldm, stream);   // G = left sol
+    NK_CUDA(h, cudaMemcpy2DAsync(A, (size_t)m * 8, Gm, (size_t)ld1 * 8, (size_t)m * 8, m, cudaMemcpyDeviceToDevice, stream));
+    if (p) NK_CUDA(h, cudaMemcpy2DAsync(B, (size_t)p * 8, Gm + m, (size_t)ld1 * 8, (size_t)p * 8, m, cudaMemcpyDeviceToDevice, stream));
+
+    // ---- reconstruction: C = GYy (gn Kmm + Gyy)^-1 S,  W = C G   (regressors.py:162-167) ----
+    double *rec = inner;           // reuse (m x ldm fits)
+    double *Lt2 = Lt;
+    double *Pt = Rt;               // (m x ldm)
+    launch2d(m, m, grid, block);
+    assemble_rec_kernel<<<grid, block, 0, stream>>>(m, gamma_n, jitter, Gyy, Kzz, rec, ldm);
+    h->launches++;
+    potrf_blocked(h, m, rec, ldm, Lt2, ldm, dinv, dinvT, dinfo, stream);
+    NK_CUDA(h, cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    NK_CUDA(h, cudaStreamSynchronize(stream));
+    if (hinfo != 0) { if (info) *info = 2; return set_err(h, NK_E_NOT_SPD, "nk_solve_abc: inner_term_rec is not positive definite (pivot " + std::to_string(hinfo) + ")"); }
+    NK_CUDA(h, cudaMemcpy2DAsync(Pt, (size_t)ldm * 8, S, (size_t)m * 8, (size_t)m * 8, m, cudaMemcpyDeviceToDevice, stream));   // S^T = S
+    trsm_fwd_t(h, m, m, rec, ldm, dinv, Pt, ldm, stream);
+    trsm_bwd_t(h, m, m, Lt2, ldm, dinvT, Pt, ldm, stream);                                       // Pt = (inner_rec^-1 S)^T
+    gemm_nt(h, d, m, m, 1.0, GYy, m, Pt, ldm, 0.0, C, m, 0.0, 0, nullptr, 0, stream);           // C = GYy P
+    gemm_nt(h, d, N1, m, 1.0, C, m, Gt, ldm, 0.0, W, N1, 0.0, 0, nullptr, 0, stream);           // W = C G
+    NK_CUDA(h, cudaGetLastError());
+    return NK_OK;
+}
+
+int nk_kernel_cross(nk_handle *h, const double *Z, long long ldz, int m, int d, const double *inv_ls, int kind,
+                    const double *X, long long ldx, long long N, double *K, long long ldk, void *stream_) {
+    if (!h) return NK_E_INVALID;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!Z || !X || !K || !inv_ls || m < 1 || d < 1 || N < 1 || N > 2000000000LL) return set_err(h, NK_E_INVALID, "nk_kernel_cross: bad argument");
+    if (kind != NK_KERNEL_RBF && kind != NK_KERNEL_MATERN52) return set_err(h, NK_E_INVALID, "nk_kernel_cross: unsupported kernel kind");
+    NK_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    const int KA = even(d + 2);
+    double *Za = dense_scratch(h, 0, (size_t)m * KA, &rc); if (rc) return rc;
+    double *Xa = dense_scratch(h, 1, (size_t)N * KA, &rc); if (rc) return rc;
+    double *ctr = dense_scratch(h, 7, (size_t)d, &rc); if (rc) return rc;
+    landmark_center(Z, ldz, m, d, ctr, stream);
+    augment_rows(h, Z, ldz, m, d, inv_ls, ctr, 1, Za, KA, stream);
+    augment_rows(h, X, ldx, N, d, inv_ls, ctr, 0, Xa, KA, stream);
+    const bool same = (Z == X && m == N);
+    gemm_nt(h, m, (int)N, KA, 1.0, Za, KA, Xa, KA, 0.0, K, ldk, 0.0, same ? (kGemmUnitDiag | kGemmLowerOnly | kGemmMirror) : 0, nullptr, 0, stream, kind);
+    NK_CUDA(h, cudaGetLastError());
+    return NK_OK;
+}
+
+int nk_kzz(nk_handle *h, const double *Z, long long ldz, int m, int d, const double *inv_ls, int kind, double *Kzz, long long ldk,
+           void *stream_) {
+    return nk_kernel_cross(h, Z, ldz, m, d, inv_ls, kind, Z, ldz, m, Kzz, ldk, stream_);
+}
+
+}  // extern "C"

@@ -1,0 +1,382 @@
+// nk_gram.cu -- the fused kernel-lift + Gram engine (reference regressors.py:141-142,147,151,153,162,164).
+//
+// What the reference does with three materialised m x n matrices (K_mn_out, K_mn_in_x, K_mn_in) and four
+// dgemm calls is done here by ONE persistent kernel per fit.  Stacking Psi = [Phi_x ; Phi_y ; U ; Y]
+// (rows: features of x_t, features of x_{t+1}, controls, next states) every Gram the fit needs is a block of
+// the symmetric product Psi Psi^T, so the work is a rank-n update of the lower triangle of a (2m+p+d)^2
+// matrix whose operand is produced on the fly:
+//
+//   pack(c)  : one 128-sample strip of chunk c -> scaled/centred/augmented sample operands for the lift GEMM
+//              ([x', -|x'|^2/2, 1] so that the accumulated value IS the exponent -r^2/2) and the raw [U;Y] rows.
+//   lift(c)  : 128 landmarks x 128 samples tile:  DMMA GEMM over d+2, kernel function in registers, tile
+//              stored straight from the C fragments into the packed feature chunk (L2-resident, evict_last).
+//   syrk(c)  : 128 x 128 output tile: DMMA contraction over the chunk's samples, accumulators added into the
+//              fragment-ordered accumulator workspace with red.global.add.f64.
+//
+// The n x m feature matrix never exists: only a double-buffered chunk of nk samples (2 x 34.6 MB at m=4096,
+// nk=512) lives in the 126 MB L2.  Work items are claimed in a fixed global order from one atomic counter;
+// items of chunk c+1's pack/lift are spliced into the middle of chunk c's syrk items, and every cross-CTA
+// dependence (pack->lift->syrk->buffer reuse, and chunk order per accumulator tile) is a monotone counter in
+// global memory, so there is no grid-wide barrier and the summation order is fixed (deterministic results).
+//
+// CTA = 8 consumer warps (2 x 4, warp tile 64 x 32, 64 FP64 accumulators per lane) + 1 producer warp that
+// claims items, resolves their dependences and feeds a 6-stage ring of 2 x 16 KB operand slabs with
+// cp.async.bulk (TMA engine, mbarrier transaction counts).
+#include "nk_gram.cuh"
+
+namespace nk {
+
+struct __align__(16) QueuedItem { int type, chunk, a, b, c, pad0, pad1, pad2; };
+
+struct GramSmemCtl {
+    uint64_t full[kGramStages];
+    uint64_t empty[kGramStages];
+    uint64_t iq_full[kItemQueue];
+    uint64_t iq_empty[kItemQueue];
+    QueuedItem iq[kItemQueue];
+};
+
+__device__ __forceinline__ void spin_until_ge(const int *ctr, int target) {
+    while (ld_acquire(ctr) < target) { __nanosleep(64); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// consumer: one 16-deep slab of the 64x32 warp tile
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_mma_slab(double (&acc)[8][4][2], const double *As, const double *Bs, int wr, int wc, int lane) {
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        double2 a[8], b[4];
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = *reinterpret_cast<const double2 *>(As + ((wr * 8 + i) * 2 + q) * kBlk + lane * 2);
+#pragma unroll
+        for (int j = 0; j < 4; j++) b[j] = *reinterpret_cast<const double2 *>(Bs + ((wc * 4 + j) * 2 + q) * kBlk + lane * 2);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack item: 128 samples -> XP, YP (lift operands) and the [U;Y] rows of Psi
+// ------------------------------------------------------------------------------------------------
+__device__ void do_pack(const GramParams &P, int chunk, int sb, int tid) {
+    const int slot = chunk & 1;
+    const int warp = tid >> 5, lane = tid & 31;
+    const long long s_base = (long long)chunk * P.nk + sb * kTile;
+    const int KL = P.KLS * kSlabK;
+    const int rp = P.nk / kPanel;  // row panels of XP / YP
+    const uint64_t pol = policy_evict_last();
+    // (1) scaled, centred, augmented operands.  one warp per sample row.
+    for (int side = 0; side < 2; side++) {
+        const double *src = side ? P.Y : P.X;
+        const long long ld = side ? P.ldy : P.ldx;
+        double *dst = side ? P.YP[slot] : P.XP[slot];
+        for (int r = warp; r < kTile; r += kConsumerWarps) {
+            const long long s = s_base + r;
+            const int row = sb * kTile + r;
+            double nrm = 0.0;
+            for (int k = lane; k < KL; k += 32) {
+                double v = 0.0;
+                if (k < P.d && s < P.n) {
+                    v = (src[s * ld + k] - P.center[k]) * P.inv_ls[k];
+                    nrm += v * v;
+                }
+                if (k < P.d || k >= P.d + 2) dst[packed_off(row, k, rp)] = v;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+            if (lane == 0) {
+                const bool live = s < P.n;
+                dst[packed_off(row, P.d, rp)] = live ? -0.5 * nrm : 0.0;
+                dst[packed_off(row, P.d + 1, rp)] = live ? 1.0 : 0.0;
+            }
+        }
+    }
+    // (2) raw [U ; Y] rows of Psi for these 128 samples (row e < p: control e; p <= e < p+d: next-state e-p)
+    double *psi = P.PSI[slot];
+    for (int e = tid; e < P.EP; e += kConsumerWarps * 32) {
+        const double *src = nullptr; long long ld = 0; int col = 0;
+        if (e < P.p) { src = P.X; ld = P.ldx; col = P.d + e; }
+        else if (e < P.p + P.d) { src = P.Y; ld = P.ldy; col = e - P.p; }
+        const int R = P.e_row0 + e;
+        for (int s8 = 0; s8 < kTile / 8; s8++) {
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const long long s = s_base + s8 * 8 + q;
+                v[q] = (src != nullptr && s < P.n) ? src[s * ld + col] : 0.0;
+            }
+            double *o = psi + packed_off(R, sb * kTile + s8 * 8, P.psi_rp);
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) st_v2_hint(o + q, v[q], v[q + 1], pol);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the persistent kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    double *stage_base = reinterpret_cast<double *>(smem_raw);
+    GramSmemCtl *ctl = reinterpret_cast<GramSmemCtl *>(smem_raw + (size_t)kGramStages * 2 * kSlabTileDoubles * 8);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < kGramStages; s++) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], kConsumerWarps); }
+        for (int s = 0; s < kItemQueue; s++) { mbar_init(&ctl->iq_full[s], 1); mbar_init(&ctl->iq_empty[s], kConsumerWarps); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int total_items = (P.n_chunks + 1) * P.period_len;
+    const int slabs_syrk = P.nk / kSlabK;
+    const int lift_warps_per_chunk = P.n_lf * kConsumerWarps;
+    const int syrk_warps_per_chunk = P.n_sy * kConsumerWarps;
+
+    if (warp >= kConsumerWarps) {
+        // =============================== producer warpgroup ===============================
+        setmaxnreg_dec<40>();
+        if (warp == kConsumerWarps && lane == 0) {
+            const uint64_t pol_keep = policy_evict_last();
+            uint32_t stage = 0, sphase = 0;   // operand ring
+            uint32_t qslot = 0, qphase = 0;   // item queue
+            for (;;) {
+                const int idx = atomicAdd(&P.counters[0], 1);
+                QueuedItem it;
+                it.type = -1; it.chunk = 0; it.a = it.b = it.c = 0; it.pad0 = it.pad1 = it.pad2 = 0;
+                bool valid = false;
+                if (idx < total_items) {
+                    const int period = idx / P.period_len - 1;
+                    const GramItem g = P.items[idx % P.period_len];
+                    const int chunk = (g.type == kItemSyrk) ? period : period + 1;
+                    if (chunk < 0 || chunk >= P.n_chunks) continue;   // item of a chunk that does not exist
+                    it.type = g.type; it.chunk = chunk; it.a = g.a; it.b = g.b; it.c = g.c;
+                    valid = true;
+                    // ---- dependences (all on items claimed earlier in the global order) ----
+                    // Counters are split by chunk parity: completions of chunk c+2 can only start after everything
+                    // of chunk c has finished (pack(c+2) waits for syrk(c)), so a per-parity count reaching its
+                    // target means exactly "all items of chunks c, c-2, ... are done".  One running total would let
+                    // early finishers of a later chunk stand in for a straggler of this one on small problems.
+                    const int par = chunk & 1, gen = chunk >> 1;
+                    if (g.type == kItemPack) {
+                        // buffers of this parity were last read by lift(chunk-2) / syrk(chunk-2)
+                        if (chunk >= 2) spin_until_ge(&P.counters[kCtrSyrk + par], gen * syrk_warps_per_chunk);
+                    } else if (g.type == kItemLift) {
+                        spin_until_ge(&P.counters[kCtrPack + par], (gen + 1) * P.n_pk);
+                    } else {
+                        spin_until_ge(&P.counters[kCtrLift + par], (gen + 1) * lift_warps_per_chunk);
+                    }
+                    fence_proxy_async();
+                }
+                // ---- publish to the consumer warps ----
+                mbar_wait(&ctl->iq_empty[qslot], qphase ^ 1);
+                ctl->iq[qslot] = it;
+                mbar_arrive(&ctl->iq_full[qslot]);   // release: consumers acquire through the wait
+                if (++qslot == kItemQueue) { qslot = 0; qphase ^= 1; }
+                if (!valid) break;
+                // ---- feed operand slabs ----
+                if (it.type == kItemPack) continue;
+                const double *Abase, *Bbase; size_t a_stride, b_stride; int nslabs;
+                const int slot = it.chunk & 1;
+                if (it.type == kItemLift) {
+                    Abase = P.ZP + (size_t)it.b * 16 * 128; a_stride = (size_t)(P.MP / kPanel) * 128;
+                    Bbase = (it.a ? P.YP[slot] : P.XP[slot]) + (size_t)it.c * 16 * 128; b_stride = (size_t)(P.nk / kPanel) * 128;
+                    nslabs = P.KLS;
+                } else {
+                    Abase = P.PSI[slot] + (size_t)it.a * 16 * 128; a_stride = (size_t)P.psi_rp * 128;
+                    Bbase = P.PSI[slot] + (size_t)it.b * 16 * 128; b_stride = a_stride;
+                    nslabs = slabs_syrk;
+                }
+                for (int s = 0; s < nslabs; s++) {
+                    mbar_wait(&ctl->empty[stage], sphase ^ 1);
+                    double *As = stage_base + (size_t)stage * 2 * kSlabTileDoubles;
+                    mbar_arrive_expect_tx(&ctl->full[stage], 2 * kSlabTileDoubles * 8);
+                    bulk_g2s(As, Abase + s * a_stride, kSlabTileDoubles * 8, &ctl->full[stage], pol_keep);
+                    bulk_g2s(As + kSlabTileDoubles, Bbase + s * b_stride, kSlabTileDoubles * 8, &ctl->full[stage], pol_keep);
+                    if (++stage == kGramStages) { stage = 0; sphase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // =============================== consumer warps ===============================
+        setmaxnreg_inc<232>();
+        const int wr = warp >> 2, wc = warp & 3;
+        const int g = lane >> 2, t = lane & 3;
+        uint32_t stage = 0, sphase = 0, qslot = 0, qphase = 0;
+        const uint64_t pol_keep = policy_evict_last();
+        const uint64_t pol_stream = policy_evict_first();
+        for (;;) {
+            mbar_wait(&ctl->iq_full[qslot], qphase);
+            const QueuedItem it = ctl->iq[qslot];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->iq_empty[qslot]);
+            if (++qslot == kItemQueue) { qslot = 0; qphase ^= 1; }
+            if (it.type < 0) break;
+
+            if (it.type == kItemPack) {
+                do_pack(P, it.chunk, it.a, tid);
+                fence_proxy_async();   // generic-proxy stores are read back through the async proxy (bulk copies)
+                __threadfence();
+                named_bar_sync(1, kConsumerWarps * 32);
+                if (tid == 0) atomicAdd(&P.counters[kCtrPack + (it.chunk & 1)], 1);
+                continue;
+            }
+
+            double acc[8][4][2];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+            const int nslabs = (it.type == kItemLift) ? P.KLS : slabs_syrk;
+            for (int s = 0; s < nslabs; s++) {
+                mbar_wait(&ctl->full[stage], sphase);
+                const double *As = stage_base + (size_t)stage * 2 * kSlabTileDoubles;
+                warp_mma_slab(acc, As, As + kSlabTileDoubles, wr, wc, lane);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->empty[stage]);
+                if (++stage == kGramStages) { stage = 0; sphase ^= 1; }
+            }
+
+            if (it.type == kItemLift) {
+                // kernel function in registers, tile stored from the C fragments into the packed chunk
+                const int slot = it.chunk & 1;
+                double *psi = P.PSI[slot];
+                const long long s_chunk = (long long)it.chunk * P.nk;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int s_local = it.c * kTile + wc * 32 + j * 8;         // first sample of this 8-column block
+                    const long long s0 = s_chunk + s_local + 2 * t;
+                    const bool live0 = s0 < P.n, live1 = (s0 + 1) < P.n;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int lm = it.b * kTile + wr * 64 + i * 8 + g;          // landmark index
+                        const bool lm_ok = lm < P.m;
+                        const double v0 = (lm_ok && live0) ? kernel_from_exponent(acc[i][j][0], P.kind) : 0.0;
+                        const double v1 = (lm_ok && live1) ? kernel_from_exponent(acc[i][j][1], P.kind) : 0.0;
+                        const int R = it.a * P.MP + it.b * kTile + wr * 64 + i * 8;   // first row of the panel
+                        double *o = psi + packed_off(R, s_local, P.psi_rp) + lane * 2;
+                        st_v2_hint(o, v0, v1, pol_keep);
+                    }
+                }
+                fence_proxy_async();
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(&P.counters[kCtrLift + (it.chunk & 1)], 1);
+            } else {
+                // add the tile into the accumulator workspace; chunk order per tile is enforced by its version
+                int *ver = &P.counters[kCounterTileVer + it.c];
+                if (lane == 0) spin_until_ge(ver, it.chunk * kConsumerWarps);
+                __syncwarp();
+                double *gt = P.Gws + (size_t)it.c * (kTile * kTile) + (size_t)warp * 32 * kBlk;
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        double *o = gt + (i * 4 + j) * kBlk + lane;
+                        red_add_f64(o, acc[i][j][0], pol_stream);
+                        red_add_f64(o + 32, acc[i][j][1], pol_stream);
+                    }
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) { atomicAdd(ver, 1); atomicAdd(&P.counters[kCtrSyrk + (it.chunk & 1)], 1); }
+            }
+        }
+    }
+}
+
+void launch_gram(const GramParams &P, int sm_count, cudaStream_t stream, cudaError_t *err) {
+    static bool configured = false;
+    if (!configured) {
+        *err = cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGramSmemBytes);
+        if (*err != cudaSuccess) return;
+        configured = true;
+    }
+    // every CTA must be resident (items wait on items claimed earlier): cooperative launch guarantees it
+    int max_blocks = 0;
+    *err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, gram_kernel, kThreads, kGramSmemBytes);
+    if (*err != cudaSuccess) return;
+    if (max_blocks < 1) { *err = cudaErrorLaunchOutOfResources; return; }
+    long long total_items = (long long)(P.n_chunks + 1) * P.period_len;
+    int grid = sm_count;
+    if (total_items < grid) grid = (int)total_items;
+    if (grid < 1) grid = 1;
+    void *args[] = {(void *)&P};
+    *err = cudaLaunchCooperativeKernel((void *)gram_kernel, dim3(grid), dim3(kThreads), args, kGramSmemBytes, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// landmark packing (once per fit): ZP rows = [z', 1, -|z'|^2/2], z' = (z - center) * inv_ls
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_landmarks_kernel(const double *Z, long long ldz, int m, int d, int MP, int KLS,
+                                      const double *inv_ls, const double *center, double *ZP) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= MP) return;
+    const int KL = KLS * kSlabK, rp = MP / kPanel;
+    double nrm = 0.0;
+    for (int k = lane; k < KL; k += 32) {
+        double v = 0.0;
+        if (k < d && row < m) { v = (Z[(long long)row * ldz + k] - center[k]) * inv_ls[k]; nrm += v * v; }
+        if (k < d || k >= d + 2) ZP[packed_off(row, k, rp)] = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    if (lane == 0) {
+        ZP[packed_off(row, d, rp)] = (row < m) ? 1.0 : 0.0;
+        ZP[packed_off(row, d + 1, rp)] = (row < m) ? -0.5 * nrm : 0.0;
+    }
+}
+
+void launch_pack_landmarks(const double *Z, long long ldz, int m, int d, int MP, int KLS, const double *inv_ls,
+                           const double *center, double *ZP, cudaStream_t stream) {
+    const int warps = 8;
+    pack_landmarks_kernel<<<(MP + warps - 1) / warps, warps * 32, 0, stream>>>(Z, ldz, m, d, MP, KLS, inv_ls, center, ZP);
+}
+
+// ------------------------------------------------------------------------------------------------
+// accumulator workspace -> row-major Grams
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double gws_read(const double *Gws, const int *tile_of, int nblk, int R, int C) {
+    // element (R, C) of Psi Psi^T, R >= C in block order guaranteed by the caller
+    const int I = R / kTile, J = C / kTile;
+    const int tile = tile_of[I * nblk + J];
+    if (tile < 0) return 0.0;
+    const int r = R % kTile, c = C % kTile;
+    const int w = (r >> 6) * 4 + (c >> 5);
+    const int i = (r & 63) >> 3, j = (c & 31) >> 3;
+    const int lane = (r & 7) * 4 + ((c & 7) >> 1);
+    return Gws[(size_t)tile * (kTile * kTile) + (size_t)((w * 32 + i * 4 + j) * 2 + (c & 1)) * 32 + lane];
+}
+
+// out(r,c) = Psi Psi^T (row0 + r, col0 + c); if the block (I,J) lies above the computed lower triangle the
+// mirrored element is read (symmetry of Psi Psi^T).
+__global__ void unpack_kernel(const double *Gws, const int *tile_of, int nblk, int row0, int col0, int rows, int cols,
+                              double *out, long long ld, int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (c >= cols || r >= rows) return;
+    int R = row0 + r, C = col0 + c;
+    if (R / kTile < C / kTile || (R / kTile == C / kTile && R < C)) { int tmp = R; R = C; C = tmp; }
+    double v = gws_read(Gws, tile_of, nblk, R, C);
+    double *o = out + (long long)r * ld + c;
+    *o = accumulate ? (*o + v) : v;
+}
+
+void launch_unpack(const double *Gws, const int *tile_of, int nblk, int row0, int col0, int rows, int cols,
+                   double *out, long long ld, int accumulate, cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0) return;
+    dim3 block(128), grid((cols + 127) / 128, rows);
+    unpack_kernel<<<grid, block, 0, stream>>>(Gws, tile_of, nblk, row0, col0, rows, cols, out, ld, accumulate);
+}
+
+}  // namespace nk

@@ -1,0 +1,45 @@
+// nk_gram.cuh -- parameter block of the fused lift+Gram engine (shared between nk_gram.cu and nk_api.cu)
+#pragma once
+#include "nk_common.cuh"
+
+namespace nk {
+
+enum ItemType : int { kItemPack = 0, kItemLift = 1, kItemSyrk = 2 };
+
+// One entry of the per-chunk work period.  pack: a = sample sub-block;  lift: a = side (0: x_t, 1: x_{t+1}),
+// b = landmark block, c = sample sub-block;  syrk: a, b = 128-row blocks of the stacked feature matrix
+// Psi = [Phi_x ; Phi_y ; U ; Y], c = accumulator tile.
+struct GramItem { int type, a, b, c; };
+
+struct GramParams {
+    const double *X; long long ldx;   // (n, d+p) row-major: state then the p controls (regressors.py:123-126)
+    const double *Y; long long ldy;   // (n, d) row-major next states
+    long long n;
+    int d, p, m, kind;
+    int MP;        // landmarks padded to a multiple of 128
+    int KLS;       // slabs of the lift contraction: ceil((d+2)/16)
+    int nk;        // samples per chunk (multiple of 128)
+    int n_chunks;
+    int psi_rp;    // row panels of Psi (= (2*MP + EP)/8)
+    int e_row0;    // first row of the [U;Y] block in Psi (= 2*MP)
+    int EP;        // [U;Y] rows padded to a multiple of 128
+    const double *ZP;       // packed, scaled, augmented landmarks: MP/8 panels x KLS slabs
+    const double *inv_ls;   // (d) 1/length_scale
+    const double *center;   // (d) shift applied to samples and landmarks before the norm expansion
+    double *XP[2], *YP[2];  // packed scaled sample operands of the lift, double-buffered per chunk parity
+    double *PSI[2];         // packed feature chunk, double-buffered: psi_rp panels x nk/16 slabs
+    double *Gws;            // accumulator tiles in C-fragment order, 16384 doubles each
+    const GramItem *items;  // one period: syrk(c) items with pack(c+1) and lift(c+1) items spliced in
+    int period_len, n_pk, n_lf, n_sy;
+    int *counters;          // [0] next item; per chunk parity: [2+par] packs done, [4+par] lift warps done, [6+par] syrk warps done; [16+t] tile versions
+};
+
+constexpr int kCtrPack = 2, kCtrLift = 4, kCtrSyrk = 6;
+constexpr int kCounterTileVer = 16;
+constexpr int kGramStages = 6;
+constexpr int kItemQueue = 4;
+constexpr size_t kGramSmemBytes = (size_t)kGramStages * 2 * kSlabTileDoubles * 8 + 1024;
+
+void launch_gram(const GramParams &P, int sm_count, cudaStream_t stream, cudaError_t *err);
+
+}  // namespace nk

@@ -1,0 +1,44 @@
+// nk_handle.cuh -- the opaque handle behind include/nk_b200.h: device, grow-only workspaces, error text.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "nk_gram.cuh"
+#include "../../include/nk_b200.h"
+
+struct nk_devbuf {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct nk_handle {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    long long launches = 0;
+
+    // ---- fused lift+Gram state (between begin and finalize) ----
+    bool gram_open = false;
+    int m = 0, d = 0, p = 0, kind = 0, nk_chunk = 0;
+    int MP = 0, KLS = 0, EP = 0, psi_rows = 0, nblk = 0, ntiles = 0;
+    int n_pk = 0, n_lf = 0, n_sy = 0, period_len = 0;
+    double last_flops = 0.0;
+    nk_devbuf zp, inv_ls, center, xp[2], yp[2], psi[2], gws, items, counters, tile_of;
+    std::vector<int> h_tile_of;
+
+    // ---- dense-stage scratch (grow-only), see nk_dense.cu ----
+    nk_devbuf dense[12];
+    nk_devbuf dinfo;
+};
+
+namespace nk {
+int set_err(nk_handle *h, int code, const std::string &msg);
+int check_cuda(nk_handle *h, cudaError_t e, const char *what);
+int ensure(nk_handle *h, nk_devbuf &b, size_t bytes);
+}  // namespace nk
+
+#define NK_CUDA(h, call)                                                     \
+    do {                                                                     \
+        int _rc = nk::check_cuda((h), (call), #call);                        \
+        if (_rc != NK_OK) return _rc;                                        \
+    } while (0)

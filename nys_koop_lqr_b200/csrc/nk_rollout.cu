@@ -1,0 +1,139 @@
+// nk_rollout.cu -- lift / predict (regressors.py:171-178, 48-55) and the batched open-loop rollout
+// (benchmark_lqr_cloth.py:18-36; _classic.py:23-41; _hjb.py:23-44) on the DMMA NT-GEMM of nk_dense.cu.
+//
+// Points (samples or trajectories) are always ROWS, so every product is C = A B^T with contraction-contiguous
+// operands: K^T = k(X, Z) (N,m) comes from the augmented-row GEMM with the kernel function as epilogue,
+// Phi^T = K^T S^-1 (S^-1 symmetric), Yhat = [Phi^T | U] W^T, and a rollout step is Z_next = Z A^T (+ U_i B^T).
+// The recurrence stays serial in time exactly like the reference loop; only trajectories are batched.
+#include "nk_dense.cuh"
+
+namespace nk {
+
+static inline int even_i(int x) { return (x + 1) & ~1; }
+
+// per-trajectory error sums for one time step: err[b] += sum_j (Yt[b,j]-Yh[b,j])^2, sim[b] += sum_j Yh[b,j]^2
+__global__ void step_error_kernel(long long nb, int d, const double *Yh, const double *Yt, double *sq_err, double *sq_sim) {
+    const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= nb) return;
+    double e = 0.0, s = 0.0;
+    for (int j = lane; j < d; j += 32) {
+        const double yh = Yh[b * d + j], df = Yt[b * d + j] - yh;
+        e += df * df; s += yh * yh;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { e += __shfl_xor_sync(0xffffffffu, e, o); s += __shfl_xor_sync(0xffffffffu, s, o); }
+    if (lane == 0) { sq_err[b] += e; sq_sim[b] += s; }
+}
+
+__global__ void copy_cols_kernel(long long rows, int cols, const double *src, long long lds, double *dst, long long ldd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = blockIdx.y;
+    if (c < cols && r < rows) dst[r * ldd + c] = src[r * lds + c];
+}
+
+// K^T = k(X, Z): (N, m), rows = points
+static int kernel_cross_t(nk_handle *h, const double *Z, long long ldz, int m, int d, const double *inv_ls, int kind,
+                          const double *X, long long ldx, long long N, double *Kt, long long ldkt, cudaStream_t stream) {
+    int rc;
+    const int KA = even_i(d + 2);
+    double *Za = dense_scratch(h, 0, (size_t)m * KA, &rc); if (rc) return rc;
+    double *Xa = dense_scratch(h, 1, (size_t)N * KA, &rc); if (rc) return rc;
+    double *ctr = dense_scratch(h, 7, (size_t)d, &rc); if (rc) return rc;
+    landmark_center(Z, ldz, m, d, ctr, stream);
+    augment_rows(h, Z, ldz, m, d, inv_ls, ctr, 1, Za, KA, stream);
+    augment_rows(h, X, ldx, N, d, inv_ls, ctr, 0, Xa, KA, stream);
+    gemm_nt(h, (int)N, m, KA, 1.0, Xa, KA, Za, KA, 0.0, Kt, ldkt, 0.0, 0, nullptr, 0, stream, kind);
+    return NK_OK;
+}
+
+}  // namespace nk
+
+using namespace nk;
+
+extern "C" {
+
+int nk_lift(nk_handle *h, const double *Z, long long ldz, int m, int d, const double *inv_ls, int kind, const double *Sinv,
+            long long ldsi, const double *X, long long ldx, long long N, double *Phi, long long ldphi, double *PhiT,
+            long long ldphit, void *stream_) {
+    if (!h) return NK_E_INVALID;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!Z || !inv_ls || !Sinv || !X || (!Phi && !PhiT) || m < 1 || d < 1 || N < 1 || N > 2000000000LL)
+        return set_err(h, NK_E_INVALID, "nk_lift: bad argument");
+    if (kind != NK_KERNEL_RBF && kind != NK_KERNEL_MATERN52) return set_err(h, NK_E_INVALID, "nk_lift: unsupported kernel kind");
+    NK_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    const int ldm = even_i(m);
+    double *Kt = dense_scratch(h, 2, (size_t)N * ldm, &rc); if (rc) return rc;
+    if ((rc = kernel_cross_t(h, Z, ldz, m, d, inv_ls, kind, X, ldx, N, Kt, ldm, stream)) != NK_OK) return rc;
+    // Phi^T (N,m) = K^T S^-1 ;  Phi (m,N) = S^-1 K  -- one product, stored both ways as requested
+    const int flags = Phi ? kGemmStoreT : 0;
+    gemm_nt(h, (int)N, m, m, 1.0, Kt, ldm, Sinv, ldsi, 0.0, PhiT, ldphit, 0.0, flags, Phi, ldphi, stream);
+    NK_CUDA(h, cudaGetLastError());
+    return NK_OK;
+}
+
+int nk_predict(nk_handle *h, const double *Z, long long ldz, int m, int d, int p, const double *inv_ls, int kind,
+               const double *Sinv, long long ldsi, const double *W, long long ldw, const double *X_aug, long long ldx, long long N,
+               double *Yhat, long long ldy, void *stream_) {
+    if (!h) return NK_E_INVALID;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!Z || !inv_ls || !Sinv || !W || !X_aug || !Yhat || m < 1 || d < 1 || p < 0 || N < 1 || N > 2000000000LL)
+        return set_err(h, NK_E_INVALID, "nk_predict: bad argument");
+    if (kind != NK_KERNEL_RBF && kind != NK_KERNEL_MATERN52) return set_err(h, NK_E_INVALID, "nk_predict: unsupported kernel kind");
+    NK_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    const int ldm = even_i(m), ldf = even_i(m + p);
+    double *Kt = dense_scratch(h, 2, (size_t)N * ldm, &rc); if (rc) return rc;
+    double *F = dense_scratch(h, 3, (size_t)N * ldf, &rc); if (rc) return rc;    // [Phi^T | U] (N, m+p)
+    if ((rc = kernel_cross_t(h, Z, ldz, m, d, inv_ls, kind, X_aug, ldx, N, Kt, ldm, stream)) != NK_OK) return rc;
+    gemm_nt(h, (int)N, m, m, 1.0, Kt, ldm, Sinv, ldsi, 0.0, F, ldf, 0.0, 0, nullptr, 0, stream);
+    if (p) {
+        dim3 block(32), grid((p + 31) / 32, (unsigned)N);
+        copy_cols_kernel<<<grid, block, 0, stream>>>(N, p, X_aug + d, ldx, F + m, ldf);
+        h->launches++;
+    }
+    gemm_nt(h, (int)N, d, m + p, 1.0, F, ldf, W, ldw, 0.0, Yhat, ldy, 0.0, 0, nullptr, 0, stream);
+    NK_CUDA(h, cudaGetLastError());
+    return NK_OK;
+}
+
+int nk_rollout(nk_handle *h, int m, int p, int d, int T, long long nb, const double *A, const double *B, const double *C,
+               const double *Z0, const double *U, double *Yhat, const double *Ytrue, double *sq_err, double *sq_sim,
+               double *Zfinal, void *stream_) {
+    if (!h) return NK_E_INVALID;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (m < 1 || p < 0 || d < 1 || T < 1 || nb < 1 || nb > 2000000000LL || !A || !C || !Z0 || (p && T > 1 && (!B || !U)))
+        return set_err(h, NK_E_INVALID, "nk_rollout: bad argument");
+    if (Ytrue && (!sq_err || !sq_sim)) return set_err(h, NK_E_INVALID, "nk_rollout: Ytrue needs sq_err and sq_sim");
+    NK_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    const int ldm = even_i(m);
+    double *Za = dense_scratch(h, 0, (size_t)nb * ldm, &rc); if (rc) return rc;
+    double *Zb = dense_scratch(h, 1, (size_t)nb * ldm, &rc); if (rc) return rc;
+    double *Ystep = nullptr;
+    if (!Yhat) { Ystep = dense_scratch(h, 2, (size_t)nb * d, &rc); if (rc) return rc; }
+    NK_CUDA(h, cudaMemcpy2DAsync(Za, (size_t)ldm * 8, Z0, (size_t)m * 8, (size_t)m * 8, nb, cudaMemcpyDeviceToDevice, stream));
+    if (Ytrue) {
+        NK_CUDA(h, cudaMemsetAsync(sq_err, 0, (size_t)nb * 8, stream));
+        NK_CUDA(h, cudaMemsetAsync(sq_sim, 0, (size_t)nb * 8, stream));
+    }
+    const int warps = 8;
+    for (int i = 0; i < T; i++) {
+        double *Yi = Yhat ? Yhat + (size_t)i * nb * d : Ystep;
+        gemm_nt(h, (int)nb, d, m, 1.0, Za, ldm, C, m, 0.0, Yi, d, 0.0, 0, nullptr, 0, stream);            // yhat_i = C z_i
+        if (Ytrue) {
+            step_error_kernel<<<(unsigned)((nb + warps - 1) / warps), warps * 32, 0, stream>>>(nb, d, Yi, Ytrue + (size_t)i * nb * d, sq_err, sq_sim);
+            h->launches++;
+        }
+        if (i == T - 1) break;
+        gemm_nt(h, (int)nb, m, m, 1.0, Za, ldm, A, m, 0.0, Zb, ldm, 0.0, 0, nullptr, 0, stream);           // z A^T
+        if (p) gemm_nt(h, (int)nb, m, p, 1.0, U + (size_t)i * nb * p, p, B, p, 1.0, Zb, ldm, 0.0, 0, nullptr, 0, stream);   // + u B^T
+        double *tmp = Za; Za = Zb; Zb = tmp;
+    }
+    if (Zfinal) NK_CUDA(h, cudaMemcpy2DAsync(Zfinal, (size_t)m * 8, Za, (size_t)ldm * 8, (size_t)m * 8, nb, cudaMemcpyDeviceToDevice, stream));
+    NK_CUDA(h, cudaGetLastError());
+    return NK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,226 @@
+"""Thin host layer over the C ABI (include/nk_b200.h): torch tensors are only device buffers + streams here.
+
+Every method takes/returns float64 CUDA tensors (row-major, contiguous) and forwards raw pointers to
+libnkb200.so.  Nothing in this module computes on the CPU; without the shared library or a B200 it raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import NK_KERNEL_MATERN52, NK_KERNEL_RBF, NkError  # noqa: F401
+
+JITTER = 1e-6  # regressors.py:120
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _f64(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+        raise TypeError(f"{name} must be a contiguous float64 CUDA tensor")
+    return t
+
+
+class Engine:
+    """One handle per (process, device).  Not thread-safe (the C handle is not)."""
+
+    _instances: dict = {}
+
+    def __init__(self, device: int | None = None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise NkError("no CUDA device: nys_koop_lqr_b200 has no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        h = C.c_void_p()
+        rc = self.lib.nk_create(C.byref(h), self.device)
+        if rc != 0:
+            raise NkError(f"nk_create failed (rc={rc}): {self.lib.nk_last_error_string(None).decode()}")
+        self.h = h
+        self.tdev = torch.device("cuda", self.device)
+
+    @classmethod
+    def get(cls, device: int | None = None) -> "Engine":
+        dev = torch.cuda.current_device() if device is None else int(device)
+        if dev not in cls._instances:
+            cls._instances[dev] = Engine(dev)
+        return cls._instances[dev]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.nk_destroy(self.h)
+            self.h = None
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)
+
+    def _ck(self, rc, what):
+        _lib.check(self.h, rc, what)
+
+    def empty(self, *shape):
+        return torch.empty(*shape, dtype=torch.float64, device=self.tdev)
+
+    def launch_count(self) -> int:
+        return int(self.lib.nk_launch_count(self.h))
+
+    def sm_count(self) -> int:
+        return int(self.lib.nk_device_sm_count(self.h))
+
+    # ------------------------------------------------------------------ fused lift + Grams
+    def gram_begin(self, Z, inv_ls, kind, p, chunk=0):
+        _f64(Z, "Z"); _f64(inv_ls, "inv_ls")
+        m, d = Z.shape
+        self._gram_shape = (m, d, int(p))
+        self._ck(self.lib.nk_gram_begin(self.h, _ptr(Z), Z.stride(0), m, d, int(p), _ptr(inv_ls), int(kind), int(chunk),
+                                        self._stream()), "nk_gram_begin")
+
+    def gram_update(self, X_aug, Y):
+        """X_aug (n, d+p) [state | controls], Y (n, d); row stride may exceed the width (views of wider buffers)."""
+        m, d, p = self._gram_shape
+        for t, nm, w in ((X_aug, "X_aug", d + p), (Y, "Y", d)):
+            if not (t.is_cuda and t.dtype == torch.float64 and t.dim() == 2 and t.shape[1] == w and t.stride(1) == 1):
+                raise TypeError(f"{nm} must be a float64 CUDA matrix with {w} unit-stride columns")
+        n = X_aug.shape[0]
+        if Y.shape[0] != n:
+            raise ValueError("X_aug and Y must have the same number of rows")
+        self._ck(self.lib.nk_gram_update(self.h, _ptr(X_aug), X_aug.stride(0), _ptr(Y), Y.stride(0), n, self._stream()),
+                 "nk_gram_update")
+
+    def gram_finalize(self, out=None, accumulate=False):
+        """Returns dict of the seven Grams (packed into one contiguous buffer `out['_flat']` for the allreduce)."""
+        m, d, p = self._gram_shape
+        sizes = dict(Gxx=(m, m), Gyx=(m, m), Gyy=(m, m), Gxu=(m, p), Gyu=(m, p), Guu=(p, p), GYy=(d, m))
+        if out is None:
+            total = sum(a * b for a, b in sizes.values())
+            flat = torch.zeros(total, dtype=torch.float64, device=self.tdev)
+            out = {"_flat": flat}
+            o = 0
+            for k, (a, b) in sizes.items():
+                out[k] = flat[o:o + a * b].view(a, b)
+                o += a * b
+        args = []
+        for k in ("Gxx", "Gyx", "Gyy", "Gxu", "Gyu", "Guu", "GYy"):
+            t = out[k]
+            args += [_ptr(t) if t.numel() else C.c_void_p(0), max(1, t.shape[1])]
+        self._ck(self.lib.nk_gram_finalize(self.h, *args, int(bool(accumulate)), self._stream()), "nk_gram_finalize")
+        return out
+
+    def grams(self, X_aug, Y, Z, inv_ls, kind, p, chunk=0):
+        self.gram_begin(Z, inv_ls, kind, p, chunk)
+        self.gram_update(X_aug, Y)
+        return self.gram_finalize()
+
+    def gram_executed_flops(self) -> float:
+        return float(self.lib.nk_gram_last_executed_flops(self.h))
+
+    # ------------------------------------------------------------------ dense stage
+    def kzz(self, Z, inv_ls, kind):
+        m, d = Z.shape
+        K = self.empty(m, m)
+        self._ck(self.lib.nk_kzz(self.h, _ptr(Z), Z.stride(0), m, d, _ptr(inv_ls), int(kind), _ptr(K), m, self._stream()), "nk_kzz")
+        return K
+
+    def kernel_cross(self, Z, X, inv_ls, kind):
+        m, d = Z.shape
+        N = X.shape[0]
+        K = self.empty(m, N)
+        self._ck(self.lib.nk_kernel_cross(self.h, _ptr(Z), Z.stride(0), m, d, _ptr(inv_ls), int(kind), _ptr(X), X.stride(0), N,
+                                          _ptr(K), N, self._stream()), "nk_kernel_cross")
+        return K
+
+    def gemm(self, A, B, transa=False, transb=False, alpha=1.0, beta=0.0, out=None):
+        _f64(A, "A"); _f64(B, "B")
+        M, K = (A.shape[1], A.shape[0]) if transa else A.shape
+        K2, N = (B.shape[1], B.shape[0]) if transb else B.shape
+        if K != K2:
+            raise ValueError("inner dimensions differ")
+        if out is None:
+            out = torch.zeros(M, N, dtype=torch.float64, device=self.tdev)
+        self._ck(self.lib.nk_gemm(self.h, int(transa), int(transb), M, N, K, float(alpha), _ptr(A), A.stride(0), _ptr(B), B.stride(0),
+                                  float(beta), _ptr(out), out.stride(0), self._stream()), "nk_gemm")
+        return out
+
+    def potrf(self, A):
+        """In-place lower Cholesky of A (n,n). Raises NkError if not SPD."""
+        _f64(A, "A")
+        info = C.c_int(0)
+        self._ck(self.lib.nk_potrf(self.h, A.shape[0], _ptr(A), A.stride(0), C.byref(info), self._stream()), "nk_potrf")
+        return A
+
+    def trsm_lower(self, L, B, trans=False):
+        _f64(L, "L"); _f64(B, "B")
+        self._ck(self.lib.nk_trsm_lower(self.h, int(trans), L.shape[0], B.shape[1], _ptr(L), L.stride(0), _ptr(B), B.stride(0),
+                                        self._stream()), "nk_trsm_lower")
+        return B
+
+    def sym_sqrt(self, K, lambda_min_bound=JITTER):
+        _f64(K, "K")
+        n = K.shape[0]
+        S, Sinv = self.empty(n, n), self.empty(n, n)
+        iters = C.c_int(0)
+        self._ck(self.lib.nk_sym_sqrt(self.h, n, _ptr(K), K.stride(0), float(lambda_min_bound), _ptr(S), n, _ptr(Sinv), n,
+                                      C.byref(iters), self._stream()), "nk_sym_sqrt")
+        self.last_sqrt_iters = iters.value
+        return S, Sinv
+
+    def solve_abc(self, G, Kzz, S, Sinv, gamma_n, jitter=JITTER):
+        m = Kzz.shape[0]
+        p = G["Guu"].shape[0]
+        d = G["GYy"].shape[0]
+        A, B, Cm, W = self.empty(m, m), self.empty(m, p), self.empty(d, m), self.empty(d, m + p)
+        info = C.c_int(0)
+        names = ("Gxx", "Gyx", "Gyy", "Gxu", "Gyu", "Guu", "GYy")
+        for k in names:
+            if G[k].numel():
+                _f64(G[k], k)
+        ptrs = [_ptr(G[k]) if G[k].numel() else C.c_void_p(0) for k in names]
+        self._ck(self.lib.nk_solve_abc(self.h, m, p, d, float(gamma_n), float(jitter), *ptrs, _ptr(_f64(Kzz, "Kzz")),
+                                       _ptr(_f64(S, "S")), _ptr(_f64(Sinv, "Sinv")), _ptr(A), _ptr(B) if p else C.c_void_p(0),
+                                       _ptr(Cm), _ptr(W), C.byref(info), self._stream()), "nk_solve_abc")
+        return A, B, Cm, W
+
+    # ------------------------------------------------------------------ lift / predict / rollout
+    def lift(self, Z, inv_ls, kind, Sinv, X_rows, transposed=False):
+        """X_rows (N,d) -> phi (m,N) (or (N,m) if transposed)."""
+        m, d = Z.shape
+        N = X_rows.shape[0]
+        if transposed:
+            out = self.empty(N, m)
+            args = (C.c_void_p(0), 0, _ptr(out), m)
+        else:
+            out = self.empty(m, N)
+            args = (_ptr(out), N, C.c_void_p(0), 0)
+        self._ck(self.lib.nk_lift(self.h, _ptr(Z), Z.stride(0), m, d, _ptr(inv_ls), int(kind), _ptr(Sinv), Sinv.stride(0),
+                                  _ptr(X_rows), X_rows.stride(0), N, *args, self._stream()), "nk_lift")
+        return out
+
+    def predict(self, Z, inv_ls, kind, Sinv, W, X_aug, p):
+        m, d = Z.shape
+        N = X_aug.shape[0]
+        out = self.empty(N, d)
+        self._ck(self.lib.nk_predict(self.h, _ptr(Z), Z.stride(0), m, d, int(p), _ptr(inv_ls), int(kind), _ptr(Sinv), Sinv.stride(0),
+                                     _ptr(W), W.stride(0), _ptr(X_aug), X_aug.stride(0), N, _ptr(out), d, self._stream()), "nk_predict")
+        return out
+
+    def rollout(self, A, B, Cm, Z0, U, Ytrue=None, return_traj=True, return_final=False):
+        """Z0 (nb,m); U (T-1,nb,p); Ytrue (T,nb,d) optional.  Returns dict(Yhat (T,nb,d), sq_err (nb), sq_sim (nb), Zfinal)."""
+        nb, m = Z0.shape
+        d = Cm.shape[0]
+        p = B.shape[1] if B is not None and B.numel() else 0
+        T = (U.shape[0] + 1) if U is not None else (Ytrue.shape[0] if Ytrue is not None else 1)
+        res = {}
+        Yhat = self.empty(T, nb, d) if return_traj else None
+        se = ss = None
+        if Ytrue is not None:
+            _f64(Ytrue, "Ytrue")
+            se, ss = self.empty(nb), self.empty(nb)
+        Zf = self.empty(nb, m) if return_final else None
+        self._ck(self.lib.nk_rollout(self.h, m, p, d, T, nb, _ptr(_f64(A, "A")), _ptr(B) if p else C.c_void_p(0), _ptr(_f64(Cm, "C")),
+                                     _ptr(_f64(Z0, "Z0")), _ptr(U) if (p and T > 1) else C.c_void_p(0), _ptr(Yhat), _ptr(Ytrue),
+                                     _ptr(se), _ptr(ss), _ptr(Zf), self._stream()), "nk_rollout")
+        res.update(Yhat=Yhat, sq_err=se, sq_sim=ss, Zfinal=Zf)
+        return res

@@ -1,0 +1,235 @@
+"""CPU oracle for the Nystrom-Koopman hot path  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this module.  The product path (``nys_koop_lqr_b200``) never does: it calls the
+sm_100a kernels through the C-ABI and raises if the extension is missing.
+
+What it is: a numpy/scipy float64 restatement of ``KoopmanNystromRegressor.fit / lift / predict``
+(reference ``regressors.py:114-178``, ``48-55``) and of the open-loop rollout ``validate_dyn_sys``
+(``benchmark_lqr_cloth.py:18-36``, ``benchmark_lqr_classic.py:23-41``, ``benchmark_lqr_hjb.py:23-44``),
+factored the way the CUDA path is factored: kernel lift -> seven data-sample Grams -> landmark
+matrices -> two regularised solves -> (A, B, C, W).
+
+Third-party arithmetic the reference delegates to (not vendored under /root/reference, versions
+unpinned by its requirements.txt -- "parity unpinned" for these):
+  * scikit-learn ``RBF.__call__`` / ``Matern.__call__`` (nu=2.5) -> ``scipy.spatial.distance.cdist``;
+    restated in ``kernel_matrix`` from the published formulas
+    (RBF: exp(-0.5*sum(((x-c)/l)^2)); Matern-5/2: (1+a+a^2/3)exp(-a), a=sqrt(5)*||(x-c)/l||).
+  * ``scipy.linalg.sqrtm / solve(assume_a='her') / lstsq`` -- ``solver='reference'`` below calls exactly
+    these in the reference's order; ``solver='chol'`` is the SPD-Cholesky statement the GPU implements.
+  * ``control.dlqr`` -> ``scipy.linalg.solve_discrete_are`` + K=(B'PB+R)^-1 B'PA (golden G4 pins it).
+
+Pinning: tests/test_oracle_vs_reference.py checks this file against the reference imported from
+/root/reference (when mounted) and tests/test_golden.py against fixtures the reference generated
+(tests/golden/make_golden.py) and against the reference's own result files G1..G4.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg
+
+RBF, MATERN52 = 0, 1
+JITTER = 1e-6  # regressors.py:120
+
+
+# --------------------------------------------------------------------------------------------
+# kernel lift  (regressors.py:139,141-144 -> sklearn kernels.py RBF / Matern nu=2.5)
+# --------------------------------------------------------------------------------------------
+def kernel_matrix(A_rows, B_rows, kind, length_scale):
+    """k(A, B) with rows = points.  Direct-difference distances like scipy cdist (no norm expansion)."""
+    A_rows = np.atleast_2d(np.asarray(A_rows, dtype=np.float64))
+    B_rows = np.atleast_2d(np.asarray(B_rows, dtype=np.float64))
+    ls = np.broadcast_to(np.asarray(length_scale, dtype=np.float64).reshape(-1), (A_rows.shape[1],)) \
+        if np.size(length_scale) in (1, A_rows.shape[1]) else None
+    if ls is None:
+        raise ValueError("length_scale must be scalar or have one entry per state dimension")
+    As = A_rows / ls
+    Bs = B_rows / ls
+    out = np.empty((As.shape[0], Bs.shape[0]))
+    # blocked over A rows so the (rows x cols x d) difference tensor stays small
+    step = max(1, int(4e6 // max(1, Bs.shape[0] * As.shape[1])))
+    for i in range(0, As.shape[0], step):
+        diff = As[i:i + step, None, :] - Bs[None, :, :]
+        out[i:i + step] = np.einsum("ijk,ijk->ij", diff, diff)
+    if kind == RBF:
+        return np.exp(-0.5 * out)
+    if kind == MATERN52:
+        a = np.sqrt(out) * np.sqrt(5.0)
+        return (1.0 + a + a * a / 3.0) * np.exp(-a)
+    raise NotImplementedError(f"kernel kind {kind}")
+
+
+# --------------------------------------------------------------------------------------------
+# the seven data-sample Grams  (regressors.py:147,151,153,162,164)
+# --------------------------------------------------------------------------------------------
+def grams(Xs, Y, U, Z, kind, length_scale, chunk=8192):
+    """Xs (n,d) states, Y (n,d) next states, U (n,p) controls, Z (m,d) landmarks.
+
+    Returns dict: Gxx = Phi_x Phi_x' (m,m), Gyx = Phi_y Phi_x' (m,m), Gyy (m,m), Gxu = Phi_x U (m,p),
+    Gyu (m,p), Guu (p,p), GYy = Y' Phi_y' (d,m); Phi_x = k(Z, Xs) (m,n), Phi_y = k(Z, Y).
+    Chunked over samples so n*m never has to exist (the reference materialises it; the sums are the same).
+    """
+    n, d = Xs.shape
+    m, p = Z.shape[0], U.shape[1]
+    G = dict(Gxx=np.zeros((m, m)), Gyx=np.zeros((m, m)), Gyy=np.zeros((m, m)), Gxu=np.zeros((m, p)),
+             Gyu=np.zeros((m, p)), Guu=np.zeros((p, p)), GYy=np.zeros((d, m)))
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        Px = kernel_matrix(Z, Xs[s:e], kind, length_scale)
+        Py = kernel_matrix(Z, Y[s:e], kind, length_scale)
+        Uc, Yc = U[s:e], Y[s:e]
+        G["Gxx"] += Px @ Px.T
+        G["Gyx"] += Py @ Px.T
+        G["Gyy"] += Py @ Py.T
+        G["Gxu"] += Px @ Uc
+        G["Gyu"] += Py @ Uc
+        G["Guu"] += Uc.T @ Uc
+        G["GYy"] += Yc.T @ Py.T
+    return G
+
+
+# --------------------------------------------------------------------------------------------
+# landmark matrices  (regressors.py:139-140,143-144,163)
+# --------------------------------------------------------------------------------------------
+def landmark_matrices(Z, kind, length_scale, sqrt="eigh"):
+    """K_zz = k(Z,Z) (no jitter, :144), K_mm = K_zz + 1e-6 I (:139,143), S = K_mm^(1/2) symmetric, S^-1."""
+    Kzz = kernel_matrix(Z, Z, kind, length_scale)
+    Kmm = Kzz + JITTER * np.eye(Z.shape[0])
+    if sqrt == "sqrtm":
+        S = scipy.linalg.sqrtm(Kmm).real
+        Sinv = None
+    else:
+        w, V = np.linalg.eigh(Kmm)
+        S = (V * np.sqrt(w)) @ V.T
+        Sinv = (V / np.sqrt(w)) @ V.T
+    return Kzz, Kmm, S, Sinv
+
+
+# --------------------------------------------------------------------------------------------
+# dense stage: Grams -> (A, B, C, W)   (regressors.py:147-169)
+# --------------------------------------------------------------------------------------------
+def solve_abc(G, Kzz, gamma_n, solver="chol"):
+    """solver='reference': scipy sqrtm / solve(assume_a='her') / lstsq in the reference's call order.
+    solver='chol': eigh root + Cholesky solves (what the sm_100a dense stage computes)."""
+    m = Kzz.shape[0]
+    p = G["Guu"].shape[0]
+    Kmm = Kzz + JITTER * np.eye(m)
+    inner = np.empty((m + p, m + p))
+    inner[:m, :m] = G["Gxx"] + gamma_n * Kmm
+    inner[:m, m:] = G["Gxu"]
+    inner[m:, :m] = G["Gxu"].T
+    inner[m:, m:] = G["Guu"] + gamma_n * np.eye(p)
+    cross = np.hstack((G["Gyx"], G["Gyu"]))  # K_mn_out @ K_mn_in.T  (:153)
+    inner_rec = gamma_n * Kmm + G["Gyy"]      # (:162)
+    if solver == "reference":
+        S = scipy.linalg.sqrtm(Kmm).real
+        right = scipy.linalg.block_diag(scipy.linalg.solve(S, Kzz.T, assume_a="her").T, np.eye(p))
+        left = scipy.linalg.solve(S, cross, assume_a="her")
+        sol = scipy.linalg.lstsq(inner, right)[0]
+        Gls = left @ sol
+        sol_rec = scipy.linalg.lstsq(inner_rec, scipy.linalg.sqrtm(Kmm).real)[0]
+        C = G["GYy"] @ sol_rec
+    elif solver == "chol":
+        w, V = np.linalg.eigh(Kmm)
+        S = (V * np.sqrt(w)) @ V.T
+        Sinv = (V / np.sqrt(w)) @ V.T
+        right = scipy.linalg.block_diag(Kzz @ Sinv, np.eye(p))
+        left = Sinv @ cross
+        sol = scipy.linalg.cho_solve(scipy.linalg.cho_factor(inner, lower=True), right)
+        Gls = left @ sol
+        sol_rec = scipy.linalg.cho_solve(scipy.linalg.cho_factor(inner_rec, lower=True), S)
+        C = G["GYy"] @ sol_rec
+    else:
+        raise ValueError(solver)
+    A, B = Gls[:, :m], Gls[:, m:]
+    W = C @ Gls
+    return A, B, C, W
+
+
+def draw_landmarks(Y, m):
+    """regressors.py:129-132 -- global legacy RNG, one draw, landmarks are NEXT-state samples. Y is (n,d)."""
+    idx = np.random.choice(np.arange(0, Y.shape[0]), size=m, replace=False)
+    return Y[idx]
+
+
+def fit(X_aug, Y, n_inputs, kind, length_scale, gamma, m=None, Z=None, solver="chol"):
+    """X_aug (n, d+p) with the p controls LAST (regressors.py:122-126), Y (n,d). Returns dict."""
+    X_aug = np.asarray(X_aug, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    n = X_aug.shape[0]
+    d = X_aug.shape[1] - n_inputs
+    if Z is None:
+        Z = draw_landmarks(Y, m)
+    G = grams(X_aug[:, :d], Y, X_aug[:, d:], Z, kind, length_scale)
+    Kzz = kernel_matrix(Z, Z, kind, length_scale)
+    A, B, C, W = solve_abc(G, Kzz, gamma * n, solver=solver)
+    return dict(A=A, B=B, C=C, W=W, Z=Z, G=G, Kzz=Kzz)
+
+
+def lift(Z, Xcols, kind, length_scale, solver="chol"):
+    """regressors.py:171-178: phi = S^-1 k(Z, X); Xcols is (d, N) column-samples; returns (m, N)."""
+    Kzz = kernel_matrix(Z, Z, kind, length_scale)
+    Kmm = Kzz + JITTER * np.eye(Z.shape[0])
+    Kmn = kernel_matrix(Z, np.asarray(Xcols).T, kind, length_scale)
+    if solver == "reference":
+        return scipy.linalg.solve(scipy.linalg.sqrtm(Kmm).real, Kmn, assume_a="her")
+    w, V = np.linalg.eigh(Kmm)
+    return (V / np.sqrt(w)) @ (V.T @ Kmn)
+
+
+def predict(W, Z, X_aug, n_inputs, kind, length_scale, solver="chol"):
+    """regressors.py:48-55: (W @ [phi(x); u]).T for X_aug (N, d+p) -> (N, d)."""
+    X_aug = np.asarray(X_aug, dtype=np.float64)
+    d = X_aug.shape[1] - n_inputs
+    phi = lift(Z, X_aug[:, :d].T, kind, length_scale, solver)
+    return (W @ np.vstack((phi, X_aug[:, d:].T))).T
+
+
+# --------------------------------------------------------------------------------------------
+# open-loop rollout  (benchmark_lqr_cloth.py:18-36 and copies)
+# --------------------------------------------------------------------------------------------
+def rollout(A, B, C, z0, controls):
+    """z0 (m,), controls (p, T-1) -> simulated states (d, T): y_0 = C z0; z_{i+1} = A z_i + B u_i."""
+    z = np.asarray(z0, dtype=np.float64).reshape(-1, 1)
+    T = controls.shape[1] + 1
+    out = np.empty((C.shape[0], T))
+    out[:, 0:1] = C @ z
+    for i in range(T - 1):
+        z = A @ z + B @ controls[:, i].reshape(-1, 1)
+        out[:, i + 1:i + 2] = C @ z
+    return out
+
+
+def rmse_cloth(true_traj, sim):
+    """benchmark_lqr_cloth.py:34"""
+    return float(np.sqrt(np.mean(np.square(true_traj - sim))))
+
+
+def rmse_percent(true_traj, sim):
+    """benchmark_lqr_classic.py:39 / benchmark_lqr_hjb.py:42 (denominator is the SIMULATED trajectory)."""
+    return float(np.sqrt(np.sum(np.square(true_traj - sim))) / np.sqrt(np.sum(np.square(sim))) * 100)
+
+
+def dlqr(A, B, Q, R):
+    """control.dlqr stand-in (benchmark_lqr_cloth.py:262): DARE + K = (B'PB+R)^-1 B'PA."""
+    P = scipy.linalg.solve_discrete_are(A, B, Q, R)
+    K = np.linalg.solve(B.T @ P @ B + R, B.T @ P @ A)
+    return K, P
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic generator of SURVEY.md section 8(d) / BASELINE.md section 3 (numpy statement; the device
+# generator in the product reproduces the same family, parity runs use this one on both sides)
+# --------------------------------------------------------------------------------------------
+def synthetic(n, d=192, p=6, seed=0):
+    rng = np.random.default_rng(seed)
+    Xs = rng.standard_normal((n, d))
+    U = rng.standard_normal((n, p))
+    M = rng.standard_normal((d, d)) * 0.9 / np.sqrt(d)
+    Bu = 0.1 * rng.standard_normal((d, p))
+    Y = np.tanh(Xs @ M.T) + U @ Bu.T
+    return Xs, U, Y
+
+
+def relerr(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(np.asarray(b)), 1e-300))

@@ -1,0 +1,218 @@
+"""GPU parity of every C-ABI entry point against the CPU oracle (oracle/nk_oracle.py) on seeded inputs.
+
+Tolerances (relative Frobenius): kernel matrices / Grams 1e-12 (north star: Gram-level gate);
+dense building blocks 1e-11..1e-12 scaled by conditioning as stated per test.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nk_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def make_problem(n, d, p, m, seed, scale=1.0):
+    rng = np.random.default_rng(seed)
+    Xs = rng.standard_normal((n, d)) * scale
+    U = rng.standard_normal((n, p))
+    M = rng.standard_normal((d, d)) * 0.9 / np.sqrt(d)
+    Bu = 0.1 * rng.standard_normal((d, p))
+    Y = np.tanh(Xs @ M.T) * scale + (U @ Bu.T if p else 0.0)
+    Z = Y[rng.choice(n, m, replace=False)]
+    return Xs, U, Y, Z
+
+
+GRAM_CASES = [
+    # n, d, p, m, kind, ls, chunk
+    (808, 192, 6, 100, O.RBF, 10.0, 0),         # cloth-like CV fold (ragged n, m not a tile multiple)
+    (3030, 192, 6, 57, O.RBF, 10.0, 256),       # cloth full, odd m, smaller chunk -> 12 chunks
+    (5000, 2, 1, 20, O.MATERN52, 1.0, 0),       # duffing-like
+    (3980, 1, 1, 100, O.MATERN52, 0.5, 0),      # hjb-like d=1
+    (1500, 7, 0, 10, O.RBF, 2.0, 128),          # no controls
+    (2100, 33, 3, 260, O.MATERN52, 4.0, 512),   # three landmark blocks
+    (127, 5, 2, 127, O.RBF, 1.5, 0),            # n < one tile, m == n
+]
+
+
+@pytest.mark.parametrize("n,d,p,m,kind,ls,chunk", GRAM_CASES)
+def test_gram_parity(engine, n, d, p, m, kind, ls, chunk):
+    Xs, U, Y, Z = make_problem(n, d, p, m, seed=n + m)
+    if kind == O.RBF and d > 3:
+        lsv = np.array([ls, ls * 1.5, ls * 0.75] * (d // 3 + 1))[:d]   # anisotropic, cycling like ThreeDimensionalKernel
+    else:
+        lsv = np.full(d, ls)
+    ref = O.grams(Xs, Y, U, Z, kind, lsv)
+    Xa = dev(np.hstack((Xs, U)))
+    G = engine.grams(Xa, dev(Y), dev(Z), dev(1.0 / lsv), kind, p, chunk)
+    torch.cuda.synchronize()
+    for k in ("Gxx", "Gyx", "Gyy", "Gxu", "Gyu", "Guu", "GYy"):
+        if ref[k].size == 0:
+            continue
+        err = O.relerr(host(G[k]), ref[k])
+        assert err <= 1e-12, f"{k}: rel err {err:.3e}"
+    # exact symmetry of the symmetric Grams (mirrored reads of one accumulator)
+    assert torch.equal(G["Gxx"], G["Gxx"].T) and torch.equal(G["Gyy"], G["Gyy"].T)
+
+
+def test_gram_streaming_and_determinism(engine):
+    """update() over sample blocks == one shot (shard-sum invariance, <=1e-13), and reruns are bit-identical."""
+    n, d, p, m = 4000, 24, 2, 150
+    Xs, U, Y, Z = make_problem(n, d, p, m, seed=5)
+    lsv = np.full(d, 3.0)
+    Xa, Yd, Zd, il = dev(np.hstack((Xs, U))), dev(Y), dev(Z), dev(1.0 / lsv)
+    G1 = engine.grams(Xa, Yd, Zd, il, O.RBF, p)
+    G1b = engine.grams(Xa, Yd, Zd, il, O.RBF, p)
+    torch.cuda.synchronize()
+    assert torch.equal(G1["_flat"], G1b["_flat"]), "fused Gram engine is not run-to-run deterministic"
+    engine.gram_begin(Zd, il, O.RBF, p)
+    for s, e in ((0, 1111), (1111, 1111), (1111, 3000), (3000, 4000)):
+        if e > s:
+            engine.gram_update(Xa[s:e], Yd[s:e])
+    G2 = engine.gram_finalize()
+    torch.cuda.synchronize()
+    for k in ("Gxx", "Gyx", "Gyy", "Gxu", "Gyu", "Guu", "GYy"):
+        assert O.relerr(host(G2[k]), host(G1[k])) <= 1e-13, k
+
+
+@pytest.mark.parametrize("m,d,kind,ls", [(100, 192, O.RBF, 10.0), (37, 2, O.MATERN52, 1.0), (300, 1, O.MATERN52, 0.3), (129, 6, O.RBF, 2.0)])
+def test_kzz_and_cross(engine, m, d, kind, ls):
+    rng = np.random.default_rng(m)
+    Z = rng.standard_normal((m, d))
+    Z[3] = Z[1]                         # coincident landmarks (r = 0 off the diagonal)
+    X = rng.standard_normal((211, d))
+    X[0] = Z[2]
+    lsv = np.full(d, ls)
+    K = host(engine.kzz(dev(Z), dev(1.0 / lsv), kind))
+    ref = O.kernel_matrix(Z, Z, kind, lsv)
+    assert np.all(np.diag(K) == 1.0)
+    assert np.array_equal(K, K.T)
+    assert np.max(np.abs(K - ref)) <= 2e-14
+    Kx = host(engine.kernel_cross(dev(Z), dev(X), dev(1.0 / lsv), kind))
+    assert np.max(np.abs(Kx - O.kernel_matrix(Z, X, kind, lsv))) <= 2e-14
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [(128, 128, 128, 0, 1), (100, 57, 33, 0, 0), (300, 260, 515, 1, 0), (7, 1000, 129, 1, 1), (513, 131, 16, 0, 1)])
+def test_gemm(engine, M, N, K, ta, tb):
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((K, M) if ta else (M, K))
+    B = rng.standard_normal((N, K) if tb else (K, N))
+    C0 = rng.standard_normal((M, N))
+    out = dev(C0)
+    engine.gemm(dev(A), dev(B), bool(ta), bool(tb), alpha=0.7, beta=-0.3, out=out)
+    ref = 0.7 * (A.T if ta else A) @ (B.T if tb else B) - 0.3 * C0
+    assert O.relerr(host(out), ref) <= 1e-14
+
+
+@pytest.mark.parametrize("n", [1, 20, 128, 129, 300, 1000])
+def test_potrf_trsm(engine, n):
+    rng = np.random.default_rng(n)
+    Q = rng.standard_normal((n, n + 5))
+    A = Q @ Q.T + n * 1e-2 * np.eye(n)
+    L = host(engine.potrf(dev(A)))
+    Lref = np.linalg.cholesky(A)
+    assert np.all(np.triu(L, 1) == 0.0)
+    assert O.relerr(L, Lref) <= 1e-12
+    B = rng.standard_normal((n, 37))
+    X0 = host(engine.trsm_lower(dev(Lref), dev(B), trans=False))
+    X1 = host(engine.trsm_lower(dev(Lref), dev(B), trans=True))
+    import scipy.linalg
+    assert O.relerr(X0, scipy.linalg.solve_triangular(Lref, B, lower=True)) <= 1e-11
+    assert O.relerr(X1, scipy.linalg.solve_triangular(Lref.T, B, lower=False)) <= 1e-11
+
+
+def test_potrf_not_spd(engine):
+    from nys_koop_lqr_b200.engine import NkError
+    A = np.eye(200)
+    A[150, 150] = -1.0
+    with pytest.raises(NkError):
+        engine.potrf(dev(A))
+
+
+@pytest.mark.parametrize("m,d,kind,ls", [(100, 192, O.RBF, 10.0), (20, 2, O.MATERN52, 1.0), (300, 8, O.RBF, 3.0), (513, 192, O.RBF, 10.0)])
+def test_sym_sqrt(engine, m, d, kind, ls):
+    """S = sqrtm(K_mm): same distance to the eigh root as scipy's sqrtm has (the oracle's own floor)."""
+    Xs, U, Y, Z = make_problem(3000, d, 1, m, seed=m)
+    lsv = np.full(d, ls)
+    Kmm = O.kernel_matrix(Z, Z, kind, lsv) + 1e-6 * np.eye(m)
+    S, Sinv = engine.sym_sqrt(dev(Kmm))
+    S, Sinv = host(S), host(Sinv)
+    w, V = np.linalg.eigh(Kmm)
+    S0 = (V * np.sqrt(w)) @ V.T
+    cond = w[-1] / w[0]
+    assert np.array_equal(S, S.T) and np.array_equal(Sinv, Sinv.T)
+    assert O.relerr(S @ S, Kmm) <= 1e-13
+    assert O.relerr(S, S0) <= 1e-15 * max(10.0, cond ** 0.5) * 10
+    assert np.linalg.norm(Sinv @ S - np.eye(m)) / np.sqrt(m) <= 1e-15 * max(10.0, cond ** 0.5) * 100
+
+
+SOLVE_CASES = [
+    (4000, 16, 2, 64, O.RBF, 4.0, 1e-4),
+    (3000, 192, 6, 100, O.RBF, 10.0, 1e-2),
+    (5000, 2, 1, 10, O.MATERN52, 1.0, 1e-6),
+    (3000, 8, 0, 130, O.RBF, 3.0, 1e-3),
+]
+
+
+@pytest.mark.parametrize("n,d,p,m,kind,ls,gamma", SOLVE_CASES)
+def test_solve_abc_vs_oracle(engine, n, d, p, m, kind, ls, gamma):
+    """Dense stage on oracle Grams: vs the Cholesky statement <=1e-9*, vs the reference-order statement (sqrtm/solve/lstsq)."""
+    Xs, U, Y, Z = make_problem(n, d, p, m, seed=m + d)
+    lsv = np.full(d, ls)
+    G = O.grams(Xs, Y, U, Z, kind, lsv)
+    Kzz = O.kernel_matrix(Z, Z, kind, lsv)
+    A0, B0, C0, W0 = O.solve_abc(G, Kzz, gamma * n, solver="chol")
+    A1, B1, C1, W1 = O.solve_abc(G, Kzz, gamma * n, solver="reference")
+    Gd = {k: dev(v) for k, v in G.items()}
+    Kd = dev(Kzz)
+    S, Sinv = engine.sym_sqrt(Kd + 1e-6 * torch.eye(m, dtype=torch.float64, device="cuda"))
+    A, B, C, W = engine.solve_abc(Gd, Kd, S, Sinv, gamma * n)
+    floor = max(O.relerr(A0, A1), 1e-12)    # distance between the two CPU statements = conditioning floor of this case
+    for name, got, r0, r1 in (("A", A, A0, A1), ("B", B, B0, B1), ("C", C, C0, C1), ("W", W, W0, W1)):
+        if r0.size == 0:
+            continue
+        e0, e1 = O.relerr(host(got), r0), O.relerr(host(got), r1)
+        assert e1 <= max(1e-9, 20 * floor), f"{name}: vs reference-order oracle {e1:.2e} (floor {floor:.2e})"
+        assert e0 <= max(1e-9, 20 * floor), f"{name}: vs cholesky oracle {e0:.2e}"
+
+
+def test_lift_predict_rollout(engine):
+    n, d, p, m = 3000, 12, 2, 80
+    Xs, U, Y, Z = make_problem(n, d, p, m, seed=11)
+    lsv = np.linspace(2.0, 4.0, d)
+    fit = O.fit(np.hstack((Xs, U)), Y, p, O.RBF, lsv, 1e-4, Z=Z, solver="chol")
+    Zd, il = dev(Z), dev(1.0 / lsv)
+    Kmm = dev(fit["Kzz"] + 1e-6 * np.eye(m))
+    S, Sinv = engine.sym_sqrt(Kmm)
+    Xq = Xs[:333]
+    phi = host(engine.lift(Zd, il, O.RBF, Sinv, dev(Xq)))
+    phi_ref = O.lift(Z, Xq.T, O.RBF, lsv)
+    assert O.relerr(phi, phi_ref) <= 1e-11
+    phiT = host(engine.lift(Zd, il, O.RBF, Sinv, dev(Xq), transposed=True))
+    assert np.array_equal(phiT.T, phi)
+    Xaq = np.hstack((Xs, U))[:333]
+    yh = host(engine.predict(Zd, il, O.RBF, Sinv, dev(fit["W"]), dev(Xaq), p))
+    assert O.relerr(yh, O.predict(fit["W"], Z, Xaq, p, O.RBF, lsv)) <= 1e-11
+    # rollout: 9 trajectories, T = 40, against the reference loop
+    nb, T = 9, 40
+    rng = np.random.default_rng(0)
+    z0 = phi_ref[:, :nb].T.copy()
+    Uc = rng.standard_normal((T - 1, nb, p))
+    Yt = rng.standard_normal((T, nb, d))
+    res = engine.rollout(dev(fit["A"]), dev(fit["B"]), dev(fit["C"]), dev(z0), dev(Uc), Ytrue=dev(Yt), return_final=True)
+    Yh = host(res["Yhat"])
+    for b in range(nb):
+        sim = O.rollout(fit["A"], fit["B"], fit["C"], z0[b], Uc[:, b, :].T)     # (d, T)
+        assert O.relerr(Yh[:, b, :].T, sim) <= 1e-12
+        se, ss = host(res["sq_err"])[b], host(res["sq_sim"])[b]
+        true = Yt[:, b, :].T
+        assert abs(np.sqrt(se / true.size) - O.rmse_cloth(true, sim)) <= 1e-12 * O.rmse_cloth(true, sim)
+        assert abs(np.sqrt(se) / np.sqrt(ss) * 100 - O.rmse_percent(true, sim)) <= 1e-12 * O.rmse_percent(true, sim)
