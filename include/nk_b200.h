@@ -48,6 +48,10 @@ int nk_gram_finalize(nk_handle *h, double *Gxx, long long ld_gxx, double *Gyx, l
 double nk_gram_last_executed_flops(nk_handle *h);
 long long nk_launch_count(nk_handle *h);
 
+/* ---- measurement aid: register-only DMMA.8x8x4 issue-rate probe (the FP64 tensor roofline denominator, measured on
+ * the device the handle is bound to).  Runs ~ms_target milliseconds, synchronises, writes TFLOP/s to *tflops (host). ---- */
+int nk_probe_dmma_tflops(nk_handle *h, double ms_target, double *tflops);
+
 /* ---- landmark kernel matrix K_zz = k(Z,Z)  (regressors.py:139,143,144,174); diagonal is exactly 1 ---- */
 int nk_kzz(nk_handle *h, const double *Z, long long ldz, int m, int d, const double *inv_ls, int kind,
            double *Kzz, long long ldk, void *stream);

@@ -41,6 +41,22 @@ __global__ void landmark_center_kernel(const double *Z, long long ldz, int m, in
     center[k] = s / m;
 }
 
+// register-only DMMA issue-rate probe: 32 independent accumulator tiles per warp, 8 warps per CTA, 2 CTAs per SM
+__global__ void __launch_bounds__(256) dmma_probe_kernel(double *out, int iters, double a0, double b0) {
+    double c[32][2];
+#pragma unroll
+    for (int i = 0; i < 32; i++) { c[i][0] = 0.0; c[i][1] = 0.0; }
+    const double a = a0 + threadIdx.x * 1e-9, b = b0;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 32; i++) dmma884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace nk
 
 using namespace nk;
@@ -87,6 +103,31 @@ const char *nk_last_error_string(nk_handle *h) { return h ? h->err.c_str() : g_c
 int nk_device_sm_count(nk_handle *h) { return h ? h->sm_count : 0; }
 double nk_gram_last_executed_flops(nk_handle *h) { return h ? h->last_flops : 0.0; }
 long long nk_launch_count(nk_handle *h) { return h ? h->launches : 0; }
+
+int nk_probe_dmma_tflops(nk_handle *h, double ms_target, double *tflops) {
+    if (!h || !tflops) return NK_E_INVALID;
+    NK_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    const int ctas = h->sm_count * 2;
+    if ((rc = ensure(h, h->dense[11], (size_t)ctas * 256 * 8)) != NK_OK) return rc;
+    cudaEvent_t e0, e1;
+    NK_CUDA(h, cudaEventCreate(&e0));
+    NK_CUDA(h, cudaEventCreate(&e1));
+    int iters = 2000;
+    float ms = 0.f;
+    for (int pass = 0; pass < 2; pass++) {     // pass 0 calibrates the loop count, pass 1 is the measurement
+        NK_CUDA(h, cudaEventRecord(e0, 0));
+        dmma_probe_kernel<<<ctas, 256>>>((double *)h->dense[11].ptr, iters, 1.0, 1e-9);
+        NK_CUDA(h, cudaEventRecord(e1, 0));
+        NK_CUDA(h, cudaEventSynchronize(e1));
+        NK_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+        if (pass == 0) { double scale = ms_target / (ms > 1e-3 ? ms : 1e-3); iters = (int)(iters * (scale < 1.0 ? 1.0 : scale)); }
+    }
+    h->launches += 2;
+    *tflops = 2.0 * 256.0 * 32.0 * (double)iters * 8.0 * ctas / (ms * 1e-3) * 1e-12;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return NK_OK;
+}
 
 int nk_gram_begin(nk_handle *h, const double *Z, long long ldz, int m, int d, int p, const double *inv_ls, int kind,
                   int chunk, void *stream_) {

@@ -41,9 +41,13 @@ class Engine:
             raise NkError(f"nk_create failed (rc={rc}): {self.lib.nk_last_error_string(None).decode()}")
         self.h = h
         self.tdev = torch.device("cuda", self.device)
+        self.gram_events = None   # set to [] to collect (start, end, n) CUDA-event triples per fused-kernel launch
 
     @classmethod
     def get(cls, device: int | None = None) -> "Engine":
+        _lib.load()
+        if not torch.cuda.is_available():
+            raise NkError("no CUDA device: nys_koop_lqr_b200 has no CPU fallback")
         dev = torch.cuda.current_device() if device is None else int(device)
         if dev not in cls._instances:
             cls._instances[dev] = Engine(dev)
@@ -67,6 +71,11 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.nk_launch_count(self.h))
 
+    def probe_dmma_tflops(self, ms_target: float = 200.0) -> float:
+        out = C.c_double(0.0)
+        self._ck(self.lib.nk_probe_dmma_tflops(self.h, float(ms_target), C.byref(out)), "nk_probe_dmma_tflops")
+        return out.value
+
     def sm_count(self) -> int:
         return int(self.lib.nk_device_sm_count(self.h))
 
@@ -87,8 +96,15 @@ class Engine:
         n = X_aug.shape[0]
         if Y.shape[0] != n:
             raise ValueError("X_aug and Y must have the same number of rows")
+        ev = None
+        if self.gram_events is not None:     # CUDA events on the launching stream around the fused kernel (bench roofline)
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(torch.cuda.current_stream(self.tdev))
         self._ck(self.lib.nk_gram_update(self.h, _ptr(X_aug), X_aug.stride(0), _ptr(Y), Y.stride(0), n, self._stream()),
                  "nk_gram_update")
+        if ev is not None:
+            ev[1].record(torch.cuda.current_stream(self.tdev))
+            self.gram_events.append((ev[0], ev[1], int(n)))
 
     def gram_finalize(self, out=None, accumulate=False):
         """Returns dict of the seven Grams (packed into one contiguous buffer `out['_flat']` for the allreduce)."""

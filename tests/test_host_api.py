@@ -1,0 +1,124 @@
+"""CPU: the drop-in surface (names, params, clone, pickle), kernel introspection, and the C-ABI library contract."""
+import ctypes
+import pathlib
+import pickle
+import re
+
+import numpy as np
+import pytest
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+
+
+def test_module_exports_reference_names():
+    import regressors as R
+    for name in ("np", "scipy", "ThreeDimensionalKernel", "KernelWrapper", "LinearKernelWrapper", "KoopmanRegressor",
+                 "KoopmanKernelRegressor", "KoopmanNystromRegressor", "KoopmanSplineRegressor"):
+        assert hasattr(R, name), name
+    ns = {}
+    exec("from regressors import *", ns)
+    assert "KoopmanNystromRegressor" in ns and "np" in ns and "scipy" in ns
+
+
+def test_constructor_params_and_clone():
+    from sklearn.base import clone
+    import regressors as R
+    k = R.ThreeDimensionalKernel(1, 10, 100, 192)
+    assert k.kernel.length_scale.shape == (1, 192)
+    assert list(np.squeeze(k.kernel.length_scale)[:4]) == [1.0, 10.0, 100.0, 1.0]
+    reg = R.KoopmanNystromRegressor(6, kernel=k, gamma=1e-7, m=100)
+    assert reg.get_params() == {"n_inputs": 6, "kernel": k, "gamma": 1e-7, "m": 100}
+    assert reg.A is None and reg.B is None and reg.C is None and reg.weights is None
+    assert reg.nystrom_centers_input is None and reg.nystrom_centers_output is None and reg.jitter == 1e-6
+    c = clone(reg)
+    assert c.get_params()["m"] == 100 and c.nystrom_centers_output is None
+    c.set_params(gamma=1e-3)
+    assert c.gamma == 1e-3
+
+
+def test_kernel_spec():
+    import regressors as R
+    from nys_koop_lqr_b200.regressors import kernel_spec
+    kind, ls = kernel_spec(R.ThreeDimensionalKernel(1, 2, 3, 7), 7)
+    assert kind == 0 and list(ls) == [1, 2, 3, 1, 2, 3, 1]
+    kind, ls = kernel_spec(R.KernelWrapper([1, 1]), 2)
+    assert kind == 1 and list(ls) == [1, 1]
+    kind, ls = kernel_spec(R.KernelWrapper(0.5), 3)
+    assert kind == 1 and list(ls) == [0.5] * 3
+    with pytest.raises(NotImplementedError):
+        kernel_spec(R.LinearKernelWrapper(1.0), 2)       # DotProduct: no GPU implementation, no CPU fallback
+    from sklearn.gaussian_process.kernels import Matern
+    with pytest.raises(NotImplementedError):
+        kernel_spec(Matern(1.0, nu=1.5), 2)
+    with pytest.raises(ValueError):
+        kernel_spec(R.KernelWrapper([1, 1, 1]), 2)
+
+
+def test_pickle_roundtrip_drops_device_state():
+    import regressors as R
+    reg = R.KoopmanNystromRegressor(1, kernel=R.KernelWrapper([1, 1]), gamma=1e-6, m=5)
+    reg.nystrom_centers_output = np.arange(10.0).reshape(2, 5)
+    reg.nystrom_centers_input = reg.nystrom_centers_output
+    reg.A = np.eye(5)
+    reg.__dict__["_dev"] = {"not": "picklable", "fn": lambda: None}
+    reg2 = pickle.loads(pickle.dumps(reg))
+    assert "_dev" not in reg2.__dict__
+    assert np.array_equal(reg2.nystrom_centers_output, reg.nystrom_centers_output) and np.array_equal(reg2.A, reg.A)
+
+
+def test_fit_argument_checks_do_not_need_gpu():
+    import regressors as R
+    reg = R.KoopmanNystromRegressor(1, kernel=R.KernelWrapper([1, 1]), gamma=1e-6, m=5)
+    with pytest.raises(ValueError):
+        reg.fit(np.zeros((10, 3)), np.zeros((9, 2)))
+    reg2 = R.KoopmanNystromRegressor(1, kernel=None, gamma=None, m=5)
+    with pytest.raises(ValueError):
+        reg2.fit(np.zeros((10, 3)), np.zeros((10, 2)))
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import regressors as R
+    from nys_koop_lqr_b200._lib import NkError
+    np.random.seed(0)
+    reg = R.KoopmanNystromRegressor(1, kernel=R.KernelWrapper([1, 1]), gamma=1e-6, m=5)
+    with pytest.raises(NkError):
+        reg.fit(np.random.rand(20, 3), np.random.rand(20, 2))
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "nk_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nk_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_c_abi_library_loads_and_exports_every_declared_symbol():
+    from nys_koop_lqr_b200 import _lib, build
+    build.build()
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    declared = _declared_symbols()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/nk_b200.h but not exported by libnkb200.so"
+    assert set(declared) == set(_lib.EXPORTED_SYMBOLS), "ctypes signatures and the header disagree"
+    lib.nk_version.restype = ctypes.c_int
+    assert lib.nk_version() >= 100
+
+
+def test_c_abi_fails_loudly_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from nys_koop_lqr_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    rc = lib.nk_create(ctypes.byref(h), 0)
+    assert rc != 0 and not h.value
+    assert b"no CUDA device" in lib.nk_last_error_string(None) or b"CUDA" in lib.nk_last_error_string(None)
+
+
+def test_out_of_scope_baselines_are_importable():
+    import regressors as R
+    assert isinstance(R.KoopmanSplineRegressor, type) and isinstance(R.KoopmanKernelRegressor, type)

@@ -1,0 +1,143 @@
+"""CPU, only where /root/reference is mounted: pins the oracle against the reference itself and its result files.
+
+G1  duffing/all_rmses_nystrom_double_dataset.csv  (forecast RMSE %, 200 seeds x 20 m)   -- m=10 column, first seeds
+G3  8x8_cloth_swing_xyz/sim_results/nystrom/data/regressor_seed_*.npy (pickled fitted estimators, m=100)
+G4  .../K_lqr_seed_*.csv (DARE gains of the stored A, B, C with Q = 0.005 C'C)
+(protocols: SURVEY.md section 4)
+"""
+import pathlib
+import pickle
+import sys
+
+import numpy as np
+import pytest
+import scipy.signal
+
+from oracle import nk_oracle as O
+
+REF = pathlib.Path("/root/reference")
+pytestmark = pytest.mark.needs_reference
+
+
+@pytest.fixture(scope="module")
+def ref():
+    sys.path.insert(0, str(REF))
+    saved = sys.modules.pop("regressors", None)
+    try:
+        import importlib
+        mod = importlib.import_module("regressors")
+        assert pathlib.Path(mod.__file__).parent == REF
+        yield mod
+    finally:
+        sys.modules.pop("regressors", None)
+        if saved is not None:
+            sys.modules["regressors"] = saved
+        sys.path.remove(str(REF))
+
+
+@pytest.mark.parametrize("kind,d", [(O.RBF, 192), (O.RBF, 3), (O.MATERN52, 2), (O.MATERN52, 1)])
+def test_kernel_matrix_vs_sklearn(ref, kind, d):
+    rng = np.random.default_rng(d)
+    A, B = rng.standard_normal((40, d)), rng.standard_normal((55, d))
+    B[0] = A[0]                                     # coincident point: r = 0
+    if kind == O.RBF:
+        holder = ref.ThreeDimensionalKernel(2.0, 3.0, 5.0, d)
+        ls = np.resize([2.0, 3.0, 5.0], d)
+    else:
+        ls = np.linspace(0.5, 1.5, d)
+        holder = ref.KernelWrapper(list(ls))
+    want = holder.kernel(A, B)
+    got = O.kernel_matrix(A, B, kind, ls)
+    assert np.max(np.abs(got - want)) <= 5e-16 * d ** 0.5 + 4e-16
+
+
+@pytest.mark.parametrize("n,d,p,m,gamma", [(2000, 12, 2, 64, 1e-2), (1500, 2, 1, 8, 1e-2), (1200, 192, 6, 40, 1e-3)])
+def test_fit_lift_predict_vs_reference(ref, n, d, p, m, gamma):
+    Xs, U, Y = O.synthetic(n, d, p, seed=n)
+    X = np.hstack((Xs, U))
+    holder = ref.ThreeDimensionalKernel(4.0, 5.0, 6.0, d)
+    ls = np.resize([4.0, 5.0, 6.0], d)
+    np.random.seed(7)
+    reg = ref.KoopmanNystromRegressor(p, kernel=holder, gamma=gamma, m=m)
+    reg.fit(X, Y)
+    Z = reg.nystrom_centers_output.T
+    np.random.seed(7)
+    assert np.array_equal(O.draw_landmarks(Y, m), Z), "landmark draw must be the reference's np.random.choice call"
+    for solver, tol in (("reference", 2e-8), ("chol", 2e-7)):   # eps * cond(inner_term): chunked vs one-shot Gram sums
+        fit = O.fit(X, Y, p, O.RBF, ls, gamma, Z=Z, solver=solver)
+        for name, want in (("A", reg.A), ("B", reg.B), ("C", reg.C), ("W", reg.weights)):
+            assert O.relerr(fit[name], want) <= tol, (solver, name, O.relerr(fit[name], want))
+    assert O.relerr(O.lift(Z, Xs[:30].T, O.RBF, ls, "reference"), reg.lift(Xs[:30].T)) <= 1e-12
+    assert O.relerr(O.predict(reg.weights, Z, X[:30], p, O.RBF, ls, "reference"), reg.predict(X[:30])) <= 1e-12
+
+
+def _duffing_data():
+    x = np.hstack((np.loadtxt(REF / "duffing/duffing_x_forced.csv", delimiter=","), np.loadtxt(REF / "duffing/duffing_x_unforced.csv", delimiter=",")))
+    nun = np.loadtxt(REF / "duffing/duffing_x_unforced.csv", delimiter=",").shape[1]
+    u = np.hstack((np.loadtxt(REF / "duffing/duffing_u_forced.csv", delimiter=",").reshape(1, -1), np.zeros((1, nun))))
+    y = np.hstack((np.loadtxt(REF / "duffing/duffing_y_forced.csv", delimiter=","), np.loadtxt(REF / "duffing/duffing_y_unforced.csv", delimiter=",")))
+    return np.vstack((x, u)).T.copy(), y.T.copy()
+
+
+def _duffing_test_traj(seed):
+    """benchmark_lqr_classic.py:122-133 with the RK4 Duffing step of dynamical_systems.py:16-48 restated."""
+    def f(x, u):
+        return -np.vstack((-x[1, :], 0.5 * x[1, :] + x[0, :] * (4 * x[0, :] ** 2 - 1) - 0.5 * u))
+    Ts = 0.01
+    np.random.seed(seed)
+    length = np.sqrt(np.random.uniform(0, 1.0)); angle = np.pi * np.random.uniform(0, 2)
+    st = np.array([length * np.cos(angle), length * np.sin(angle)]).reshape(-1, 1)
+    us = 1.0 * scipy.signal.square(2 * np.pi * 10 / 3 * np.linspace(0, 2, 100))
+    traj = st.copy()
+    for u in us:
+        k1 = f(st, u); k2 = f(st + k1 * Ts / 2, u); k3 = f(st + k2 * Ts / 2, u); k4 = f(st + k1 * Ts, u)
+        st = st + (Ts / 6) * (k1 + 2 * k2 + 2 * k3 + k4)
+        traj = np.hstack((traj, st))
+    return traj, us.reshape(1, -1)
+
+
+def test_golden_G1_duffing_rmse_column_m10():
+    """Whole path fit -> lift -> rollout -> RMSE% against the reference's result CSV (two-draw RNG quirk)."""
+    want = np.loadtxt(REF / "duffing/all_rmses_nystrom_double_dataset.csv")
+    X, Y = _duffing_data()
+    errs = []
+    for seed in range(4):
+        traj, ctrl = _duffing_test_traj(seed)
+        np.random.seed(seed)
+        idx = np.random.choice(np.arange(0, X.shape[0]), size=10, replace=False)
+        np.random.choice(np.arange(0, X.shape[0]), size=10, replace=False)      # second draw, discarded (older fit)
+        Z = Y[idx]
+        fit = O.fit(X, Y, 1, O.MATERN52, [1.0, 1.0], 1e-6, Z=Z, solver="chol")
+        z0 = O.lift(Z, traj[:, :1], O.MATERN52, [1.0, 1.0])[:, 0]
+        got = O.rmse_percent(traj, O.rollout(fit["A"], fit["B"], fit["C"], z0, ctrl))
+        errs.append(abs(got - want[seed, 0]) / want[seed, 0])
+    assert max(errs) <= 1e-6, errs          # 6 significant digits
+
+
+def test_golden_G3_G4_cloth_pickles_and_gains():
+    data = REF / "8x8_cloth_swing_xyz/sim_results/nystrom/data"
+    sys.path.insert(0, str(REF))
+    try:
+        with open(data / "regressor_seed_0.npy", "rb") as f:
+            reg = pickle.load(f)
+    finally:
+        sys.path.remove(str(REF))
+        sys.modules.pop("regressors", None)
+    A, B, C = reg.A, reg.B, reg.C
+    assert A.shape == (100, 100) and B.shape == (100, 6) and C.shape == (192, 100)
+    # G4: gain of the stored model with Q = 0.005 C'C, rows permuted for the MATLAB simulator (benchmark_lqr_cloth.py:263)
+    Q = 0.005 * C.T @ C
+    K, _ = O.dlqr(A, B, (Q + Q.T) / 2, np.eye(6))
+    want = np.loadtxt(data / "K_lqr_seed_0.csv")
+    assert O.relerr(K[[0, 3, 1, 4, 2, 5], :], want) <= 1e-8
+    # G3: refit with the stored landmarks on the script's training set lands on the conditioning floor (~1e-4)
+    p = REF / "8x8_cloth_swing_xyz"
+    trajs = [np.loadtxt(p / f"state_samples_cloth_swing_{i}.csv", delimiter=",").T for i in range(10, 40)]
+    ctrls = [np.loadtxt(p / f"input_samples_cloth_swing_{i}.csv", delimiter=",")[:, :6].T for i in range(10, 40)]
+    X = np.hstack([np.vstack((t[:, :-1], c[:, :-1])) for t, c in zip(trajs, ctrls)]).T
+    Y = np.hstack([t[:, 1:] for t in trajs]).T
+    np.random.seed(0)
+    Z = Y[np.random.choice(np.arange(0, 3030), 100, False)]
+    assert np.array_equal(Z.T, reg.nystrom_centers_output)
+    fit = O.fit(X, Y, 6, O.RBF, np.full(192, 10.0), 1e-7, Z=Z, solver="reference")
+    assert O.relerr(fit["A"], A) <= 5e-3 and O.relerr(fit["B"], B) <= 5e-4 and O.relerr(fit["C"], C) <= 5e-3
