@@ -305,7 +305,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--samples", "--n-samples", dest="n", type=int, default=10_000_000)
     ap.add_argument("--m", type=int, default=4096)
     ap.add_argument("--d", type=int, default=192)
     ap.add_argument("--p", type=int, default=6)
