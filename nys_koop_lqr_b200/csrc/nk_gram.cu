@@ -11,7 +11,7 @@
 //   lift(c)  : 128 landmarks x 128 samples tile:  DMMA GEMM over d+2, kernel function in registers, tile
 //              stored straight from the C fragments into the packed feature chunk (L2-resident, evict_last).
 //   syrk(c)  : 128 x 128 output tile: DMMA contraction over the chunk's samples, accumulators added into the
-//              fragment-ordered accumulator workspace with red.global.add.f64.
+//              fragment-ordered accumulator workspace with cp.reduce.async.bulk ... add.f64 (UBLKRED).
 //
 // The n x m feature matrix never exists: only a double-buffered chunk of nk samples (2 x 34.6 MB at m=4096,
 // nk=512) lives in the 126 MB L2.  Work items are claimed in a fixed global order from one atomic counter;
@@ -20,8 +20,9 @@
 // global memory, so there is no grid-wide barrier and the summation order is fixed (deterministic results).
 //
 // CTA = 8 consumer warps (2 x 4, warp tile 64 x 32, 64 FP64 accumulators per lane) + 1 producer warp that
-// claims items, resolves their dependences and feeds a 6-stage ring of 2 x 16 KB operand slabs with
-// cp.async.bulk (TMA engine, mbarrier transaction counts).
+// claims items one ahead, resolves their dependences and feeds a 3-stage ring of 2 x 16 KB operand slabs with
+// cp.async.bulk (TMA engine, mbarrier transaction counts); 128 KB of shared memory stage the accumulator tiles
+// for the asynchronous bulk reduce-add of the Gram epilogue.
 #include "nk_gram.cuh"
 
 namespace nk {
@@ -120,12 +121,53 @@ __device__ void do_pack(const GramParams &P, int chunk, int sb, int tid) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// raw 32-bit shared-address helpers (addresses are computed once; the generic->shared conversion of a pointer
+// costs an S2R + LEA each time the compiler rematerialises it inside the slab loop)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_test_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    while (!mbar_test_a(bar, parity)) {}
+}
+__device__ __forceinline__ double2 lds_v2(uint32_t addr) {
+    double2 v;
+    asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, double a, double b) {
+    asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ uint32_t opaque(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+
+// one k8 step (two DMMA k4 steps) of the 64x32 warp tile; a0 and b[] were prefetched, a[1..7] are loaded here
+__device__ __forceinline__ void k8_step(double (&acc)[8][4][2], uint32_t aq, double2 a0, const double2 (&b)[4]) {
+    double2 a[8];
+    a[0] = a0;
+#pragma unroll
+    for (int i = 1; i < 8; i++) a[i] = lds_v2(aq + i * 1024);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // the persistent kernel
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     double *stage_base = reinterpret_cast<double *>(smem_raw);
-    GramSmemCtl *ctl = reinterpret_cast<GramSmemCtl *>(smem_raw + (size_t)kGramStages * 2 * kSlabTileDoubles * 8);
+    GramSmemCtl *ctl = reinterpret_cast<GramSmemCtl *>(smem_raw + kGramStageBytes + kGramStagingBytes);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -149,28 +191,35 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
             const uint64_t pol_keep = policy_evict_last();
             uint32_t stage = 0, sphase = 0;   // operand ring
             uint32_t qslot = 0, qphase = 0;   // item queue
-            for (;;) {
-                const int idx = atomicAdd(&P.counters[0], 1);
-                QueuedItem it;
-                it.type = -1; it.chunk = 0; it.a = it.b = it.c = 0; it.pad0 = it.pad1 = it.pad2 = 0;
-                bool valid = false;
-                if (idx < total_items) {
+            // claim(): next existing item in the global order (items of chunks that do not exist are skipped)
+            auto claim = [&](QueuedItem &it) -> bool {
+                for (;;) {
+                    const int idx = atomicAdd(&P.counters[0], 1);
+                    if (idx >= total_items) { it.type = -1; return false; }
                     const int period = idx / P.period_len - 1;
                     const GramItem g = P.items[idx % P.period_len];
                     const int chunk = (g.type == kItemSyrk) ? period : period + 1;
-                    if (chunk < 0 || chunk >= P.n_chunks) continue;   // item of a chunk that does not exist
+                    if (chunk < 0 || chunk >= P.n_chunks) continue;
                     it.type = g.type; it.chunk = chunk; it.a = g.a; it.b = g.b; it.c = g.c;
-                    valid = true;
+                    return true;
+                }
+            };
+            QueuedItem it, nxt;
+            it.pad0 = it.pad1 = it.pad2 = 0; it.chunk = it.a = it.b = it.c = 0;
+            nxt = it;
+            bool valid = claim(it);
+            for (;;) {
+                if (valid) {
                     // ---- dependences (all on items claimed earlier in the global order) ----
                     // Counters are split by chunk parity: completions of chunk c+2 can only start after everything
                     // of chunk c has finished (pack(c+2) waits for syrk(c)), so a per-parity count reaching its
                     // target means exactly "all items of chunks c, c-2, ... are done".  One running total would let
                     // early finishers of a later chunk stand in for a straggler of this one on small problems.
-                    const int par = chunk & 1, gen = chunk >> 1;
-                    if (g.type == kItemPack) {
+                    const int par = it.chunk & 1, gen = it.chunk >> 1;
+                    if (it.type == kItemPack) {
                         // buffers of this parity were last read by lift(chunk-2) / syrk(chunk-2)
-                        if (chunk >= 2) spin_until_ge(&P.counters[kCtrSyrk + par], gen * syrk_warps_per_chunk);
-                    } else if (g.type == kItemLift) {
+                        if (it.chunk >= 2) spin_until_ge(&P.counters[kCtrSyrk + par], gen * syrk_warps_per_chunk);
+                    } else if (it.type == kItemLift) {
                         spin_until_ge(&P.counters[kCtrPack + par], (gen + 1) * P.n_pk);
                     } else {
                         spin_until_ge(&P.counters[kCtrLift + par], (gen + 1) * lift_warps_per_chunk);
@@ -183,27 +232,31 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                 mbar_arrive(&ctl->iq_full[qslot]);   // release: consumers acquire through the wait
                 if (++qslot == kItemQueue) { qslot = 0; qphase ^= 1; }
                 if (!valid) break;
+                // claim the following item now, so that its round trip overlaps with feeding this one
+                const bool nvalid = claim(nxt);
                 // ---- feed operand slabs ----
-                if (it.type == kItemPack) continue;
-                const double *Abase, *Bbase; size_t a_stride, b_stride; int nslabs;
-                const int slot = it.chunk & 1;
-                if (it.type == kItemLift) {
-                    Abase = P.ZP + (size_t)it.b * 16 * 128; a_stride = (size_t)(P.MP / kPanel) * 128;
-                    Bbase = (it.a ? P.YP[slot] : P.XP[slot]) + (size_t)it.c * 16 * 128; b_stride = (size_t)(P.nk / kPanel) * 128;
-                    nslabs = P.KLS;
-                } else {
-                    Abase = P.PSI[slot] + (size_t)it.a * 16 * 128; a_stride = (size_t)P.psi_rp * 128;
-                    Bbase = P.PSI[slot] + (size_t)it.b * 16 * 128; b_stride = a_stride;
-                    nslabs = slabs_syrk;
+                if (it.type != kItemPack) {
+                    const double *Abase, *Bbase; size_t a_stride, b_stride; int nslabs;
+                    const int slot = it.chunk & 1;
+                    if (it.type == kItemLift) {
+                        Abase = P.ZP + (size_t)it.b * 16 * 128; a_stride = (size_t)(P.MP / kPanel) * 128;
+                        Bbase = (it.a ? P.YP[slot] : P.XP[slot]) + (size_t)it.c * 16 * 128; b_stride = (size_t)(P.nk / kPanel) * 128;
+                        nslabs = P.KLS;
+                    } else {
+                        Abase = P.PSI[slot] + (size_t)it.a * 16 * 128; a_stride = (size_t)P.psi_rp * 128;
+                        Bbase = P.PSI[slot] + (size_t)it.b * 16 * 128; b_stride = a_stride;
+                        nslabs = slabs_syrk;
+                    }
+                    for (int s = 0; s < nslabs; s++) {
+                        mbar_wait(&ctl->empty[stage], sphase ^ 1);
+                        double *As = stage_base + (size_t)stage * 2 * kSlabTileDoubles;
+                        mbar_arrive_expect_tx(&ctl->full[stage], 2 * kSlabTileDoubles * 8);
+                        bulk_g2s(As, Abase + s * a_stride, kSlabTileDoubles * 8, &ctl->full[stage], pol_keep);
+                        bulk_g2s(As + kSlabTileDoubles, Bbase + s * b_stride, kSlabTileDoubles * 8, &ctl->full[stage], pol_keep);
+                        if (++stage == kGramStages) { stage = 0; sphase ^= 1; }
+                    }
                 }
-                for (int s = 0; s < nslabs; s++) {
-                    mbar_wait(&ctl->empty[stage], sphase ^ 1);
-                    double *As = stage_base + (size_t)stage * 2 * kSlabTileDoubles;
-                    mbar_arrive_expect_tx(&ctl->full[stage], 2 * kSlabTileDoubles * 8);
-                    bulk_g2s(As, Abase + s * a_stride, kSlabTileDoubles * 8, &ctl->full[stage], pol_keep);
-                    bulk_g2s(As + kSlabTileDoubles, Bbase + s * b_stride, kSlabTileDoubles * 8, &ctl->full[stage], pol_keep);
-                    if (++stage == kGramStages) { stage = 0; sphase ^= 1; }
-                }
+                it = nxt; valid = nvalid;
             }
         }
     } else {
@@ -213,16 +266,40 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
         const int g = lane >> 2, t = lane & 3;
         uint32_t stage = 0, sphase = 0, qslot = 0, qphase = 0;
         const uint64_t pol_keep = policy_evict_last();
-        const uint64_t pol_stream = policy_evict_first();
+        // shared-window addresses, computed once
+        const uint32_t sm0 = opaque(smem_u32(smem_raw));
+        const uint32_t a_off = opaque(sm0 + (uint32_t)(wr * 8 * 2) * 512u + lane * 16u);            // A fragment (i=0,q=0) of stage 0
+        const uint32_t b_off = opaque(sm0 + 16384u + (uint32_t)(wc * 4 * 2) * 512u + lane * 16u);  // B fragment (j=0,q=0) of stage 0
+        const uint32_t full0 = opaque(smem_u32(&ctl->full[0])), empty0 = opaque(smem_u32(&ctl->empty[0]));
+        const uint32_t stg = opaque(sm0 + (uint32_t)kGramStageBytes + (uint32_t)warp * 16384u);  // this warp's 16 KB accumulator staging
+        // deferred completion signal of the previous syrk item of this warp (its bulk reduce is asynchronous)
+        int *pend_ver = nullptr;
+        int pend_par = 0;
+        auto flush_pending = [&]() {
+            if (pend_ver != nullptr) {
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    __threadfence();
+                    atomicAdd(pend_ver, 1);
+                    atomicAdd(&P.counters[kCtrSyrk + pend_par], 1);
+                }
+                __syncwarp();
+                pend_ver = nullptr;
+            }
+        };
         for (;;) {
-            mbar_wait(&ctl->iq_full[qslot], qphase);
+            if (!mbar_try_wait(&ctl->iq_full[qslot], qphase)) {
+                flush_pending();      // never sit on a completion signal while idle: later items may be waiting for it
+                mbar_wait(&ctl->iq_full[qslot], qphase);
+            }
             const QueuedItem it = ctl->iq[qslot];
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->iq_empty[qslot]);
             if (++qslot == kItemQueue) { qslot = 0; qphase ^= 1; }
-            if (it.type < 0) break;
+            if (it.type < 0) { flush_pending(); break; }
 
             if (it.type == kItemPack) {
+                flush_pending();
                 do_pack(P, it.chunk, it.a, tid);
                 fence_proxy_async();   // generic-proxy stores are read back through the async proxy (bulk copies)
                 __threadfence();
@@ -237,16 +314,49 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
+            // ---- main loop: k8 steps with the first fragments of the NEXT step (and next slab) prefetched ----
             const int nslabs = (it.type == kItemLift) ? P.KLS : slabs_syrk;
+            mbar_wait_a(full0 + stage * 8, sphase);
+            double2 b[4], nb[4], a0, na0;
+            {
+                const uint32_t so = stage * (uint32_t)(2 * kSlabTileDoubles * 8);
+#pragma unroll
+                for (int j = 0; j < 4; j++) b[j] = lds_v2(b_off + so + j * 1024);
+                a0 = lds_v2(a_off + so);
+            }
             for (int s = 0; s < nslabs; s++) {
-                mbar_wait(&ctl->full[stage], sphase);
-                const double *As = stage_base + (size_t)stage * 2 * kSlabTileDoubles;
-                warp_mma_slab(acc, As, As + kSlabTileDoubles, wr, wc, lane);
+                const uint32_t so = stage * (uint32_t)(2 * kSlabTileDoubles * 8);
+                uint32_t nstage = stage + 1, nphase = sphase;
+                if (nstage == kGramStages) { nstage = 0; nphase ^= 1; }
+                const bool has_next = (s + 1 < nslabs);
+                // early, non-blocking look at the next slab's barrier (its result is consumed after the q=0 DMMAs)
+                uint32_t ready = has_next ? mbar_test_a(full0 + nstage * 8, nphase) : 1u;
+                // q = 0 (prefetch q = 1 of this slab)
+#pragma unroll
+                for (int j = 0; j < 4; j++) nb[j] = lds_v2(b_off + so + 512 + j * 1024);
+                na0 = lds_v2(a_off + so + 512);
+                k8_step(acc, a_off + so, a0, b);
+#pragma unroll
+                for (int j = 0; j < 4; j++) b[j] = nb[j];
+                a0 = na0;
+                // q = 1 (prefetch q = 0 of the next slab)
+                if (has_next) {
+                    if (!ready) mbar_wait_a(full0 + nstage * 8, nphase);
+                    const uint32_t no = nstage * (uint32_t)(2 * kSlabTileDoubles * 8);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) nb[j] = lds_v2(b_off + no + j * 1024);
+                    na0 = lds_v2(a_off + no);
+                }
+                k8_step(acc, a_off + so + 512, a0, b);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&ctl->empty[stage]);
-                if (++stage == kGramStages) { stage = 0; sphase ^= 1; }
+                if (lane == 0) mbar_arrive_a(empty0 + stage * 8);
+#pragma unroll
+                for (int j = 0; j < 4; j++) b[j] = nb[j];
+                a0 = na0;
+                stage = nstage; sphase = nphase;
             }
 
+            flush_pending();
             if (it.type == kItemLift) {
                 // kernel function in registers, tile stored from the C fragments into the packed chunk
                 const int slot = it.chunk & 1;
@@ -273,22 +383,26 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                 __syncwarp();
                 if (lane == 0) atomicAdd(&P.counters[kCtrLift + (it.chunk & 1)], 1);
             } else {
-                // add the tile into the accumulator workspace; chunk order per tile is enforced by its version
+                // Gram epilogue: accumulators -> this warp's 16 KB staging buffer -> one asynchronous bulk reduce-add
+                // (TMA engine, SASS UBLKRED.ADD.F64) into the fragment-ordered accumulator tile.  The warp does not wait
+                // for it: the completion signal is sent when the next item's main loop is over (flush_pending).  Chunk
+                // order per tile is enforced by the tile's version counter, so the summation order is fixed.
                 int *ver = &P.counters[kCounterTileVer + it.c];
-                if (lane == 0) spin_until_ge(ver, it.chunk * kConsumerWarps);
-                __syncwarp();
-                double *gt = P.Gws + (size_t)it.c * (kTile * kTile) + (size_t)warp * 32 * kBlk;
 #pragma unroll
                 for (int i = 0; i < 8; i++)
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        double *o = gt + (i * 4 + j) * kBlk + lane;
-                        red_add_f64(o, acc[i][j][0], pol_stream);
-                        red_add_f64(o + 32, acc[i][j][1], pol_stream);
-                    }
-                __threadfence();
+                    for (int j = 0; j < 4; j++) sts_v2(stg + (uint32_t)(i * 4 + j) * 512u + lane * 16u, acc[i][j][0], acc[i][j][1]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) { atomicAdd(ver, 1); atomicAdd(&P.counters[kCtrSyrk + (it.chunk & 1)], 1); }
+                if (lane == 0) {
+                    spin_until_ge(ver, it.chunk * kConsumerWarps);
+                    double *gt = P.Gws + (size_t)it.c * (kTile * kTile) + (size_t)warp * 32 * kBlk;
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
+                                 ::"l"(gt), "r"(stg), "r"(16384) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                pend_ver = ver;
+                pend_par = it.chunk & 1;
             }
         }
     }
@@ -355,7 +469,7 @@ __device__ __forceinline__ double gws_read(const double *Gws, const int *tile_of
     const int w = (r >> 6) * 4 + (c >> 5);
     const int i = (r & 63) >> 3, j = (c & 31) >> 3;
     const int lane = (r & 7) * 4 + ((c & 7) >> 1);
-    return Gws[(size_t)tile * (kTile * kTile) + (size_t)((w * 32 + i * 4 + j) * 2 + (c & 1)) * 32 + lane];
+    return Gws[(size_t)tile * (kTile * kTile) + (size_t)(w * 32 + i * 4 + j) * 64 + lane * 2 + (c & 1)];
 }
 
 // out(r,c) = Psi Psi^T (row0 + r, col0 + c); if the block (I,J) lies above the computed lower triangle the

@@ -36,9 +36,11 @@ struct GramParams {
 
 constexpr int kCtrPack = 2, kCtrLift = 4, kCtrSyrk = 6;
 constexpr int kCounterTileVer = 16;
-constexpr int kGramStages = 6;
+constexpr int kGramStages = 3;
 constexpr int kItemQueue = 4;
-constexpr size_t kGramSmemBytes = (size_t)kGramStages * 2 * kSlabTileDoubles * 8 + 1024;
+constexpr size_t kGramStageBytes = (size_t)kGramStages * 2 * kSlabTileDoubles * 8;      // 96 KB operand ring
+constexpr size_t kGramStagingBytes = (size_t)kConsumerWarps * 16384;                    // 128 KB accumulator staging
+constexpr size_t kGramSmemBytes = kGramStageBytes + kGramStagingBytes + 512;
 
 void launch_gram(const GramParams &P, int sm_count, cudaStream_t stream, cudaError_t *err);
 

@@ -91,7 +91,7 @@ class Engine:
         """X_aug (n, d+p) [state | controls], Y (n, d); row stride may exceed the width (views of wider buffers)."""
         m, d, p = self._gram_shape
         for t, nm, w in ((X_aug, "X_aug", d + p), (Y, "Y", d)):
-            if not (t.is_cuda and t.dtype == torch.float64 and t.dim() == 2 and t.shape[1] == w and t.stride(1) == 1):
+            if not (t.is_cuda and t.dtype == torch.float64 and t.dim() == 2 and t.shape[1] == w and (t.stride(1) == 1 or w == 1)):
                 raise TypeError(f"{nm} must be a float64 CUDA matrix with {w} unit-stride columns")
         n = X_aug.shape[0]
         if Y.shape[0] != n:

@@ -59,17 +59,21 @@ def install_shims():
 
         def __iter__(self):
             return iter(())
+    def _attr(name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Noop()
     mpl = types.ModuleType("matplotlib")
     mpl.use = lambda *a, **k: None
-    mpl.__getattr__ = lambda name: _Noop()
+    mpl.__getattr__ = _attr
     plt = types.ModuleType("matplotlib.pyplot")
-    plt.__getattr__ = lambda name: _Noop()
+    plt.__getattr__ = _attr
     mpl.pyplot = plt
     sys.modules["matplotlib"] = mpl
     sys.modules["matplotlib.pyplot"] = plt
     for sub in ("animation", "cm", "colors", "ticker"):
         m = types.ModuleType(f"matplotlib.{sub}")
-        m.__getattr__ = lambda name: _Noop()
+        m.__getattr__ = _attr
         sys.modules[f"matplotlib.{sub}"] = m
         setattr(mpl, sub, m)
 
@@ -143,6 +147,46 @@ def compare_model(rep, script, config, pair):
     for k in ("A", "B", "C"):
         rep.add(script, config, k, relerr(getattr(pair["b200"], k), getattr(pair["ref"], k)), pair["floor"][k])
     rep.timing.append(dict(script=script, config=config, ref_fit_s=pair["ref_s"], b200_fit_s=pair["b200_s"]))
+
+
+def solver_study(rep, script, config, pair, X, Y, kind, ls, gamma):
+    """Where the B200 result sits far above the reference's self-floor: separate Gram error from solver-algorithm error.
+    (1) the GPU Grams pushed through the reference's own scipy sqrtm/solve/lstsq sequence (oracle, verification only) must land
+    on the reference's floor; (2) both answers against a high-precision solve of the same float64 system (Cholesky + iterative
+    refinement with long-double residuals): the SPD-Cholesky dense stage is the more accurate of the two."""
+    import torch
+    from oracle import nk_oracle as O
+    from nys_koop_lqr_b200.engine import Engine
+    eng = Engine.get()
+    ref, b2 = pair["ref"], pair["b200"]
+    d = Y.shape[0]
+    p = X.shape[0] - d
+    Z = np.ascontiguousarray(np.asarray(ref.nystrom_centers_output).T)
+    n = X.shape[1]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    G = eng.grams(t(X.T), t(Y.T), t(Z), t(1.0 / np.asarray(ls, dtype=float)), kind, p)
+    Gh = {k: v.cpu().numpy() for k, v in G.items() if k != "_flat"}
+    Kzz = O.kernel_matrix(Z, Z, kind, ls)
+    A1, B1, C1, _ = O.solve_abc(Gh, Kzz, gamma * n, solver="reference")
+    rep.add(script, config, "A: GPU Grams -> reference's scipy sqrtm/solve/lstsq (verification mode)", relerr(A1, ref.A), pair["floor"]["A"])
+    rep.add(script, config, "C: GPU Grams -> reference's scipy sqrtm/solve/lstsq (verification mode)", relerr(C1, ref.C), pair["floor"]["C"])
+    # high-precision solve of inner * sol = right
+    m = Z.shape[0]
+    Kmm = Kzz + 1e-6 * np.eye(m)
+    w, V = np.linalg.eigh(Kmm)
+    Sinv = (V / np.sqrt(w)) @ V.T
+    inner = np.block([[Gh["Gxx"] + gamma * n * Kmm, Gh["Gxu"]], [Gh["Gxu"].T, Gh["Guu"] + gamma * n * np.eye(p)]])
+    right = scipy.linalg.block_diag(Kzz @ Sinv, np.eye(p))
+    left = Sinv @ np.hstack((Gh["Gyx"], Gh["Gyu"]))
+    cf = scipy.linalg.cho_factor(inner, lower=True)
+    sol = scipy.linalg.cho_solve(cf, right)
+    iL, rL = inner.astype(np.longdouble), right.astype(np.longdouble)
+    for _ in range(40):
+        res = (rL - iL @ sol.astype(np.longdouble)).astype(np.float64)
+        sol = sol + scipy.linalg.cho_solve(cf, res)
+    A_hp = (left @ sol)[:, :m]
+    rep.add(script, config, "A vs high-precision solve: reference (lstsq/gelsd)", relerr(ref.A, A_hp), note=f"cond(inner)={np.linalg.cond(inner):.1e}")
+    rep.add(script, config, "A vs high-precision solve: B200 (Cholesky)", relerr(b2.A, A_hp))
 
 
 def gain_of(mod, reg, qscale):
@@ -242,6 +286,7 @@ def run_cloth(rep, quick):
     make = lambda mod: mod.KoopmanNystromRegressor(6, kernel=mod.ThreeDimensionalKernel(10, 10, 10, 192), gamma=1e-7, m=100)
     pair = fit_pair(mods, make, X, Y, 0)
     compare_model(rep, "cloth", "LQR seed=0 m=100", pair)
+    solver_study(rep, "cloth", "LQR seed=0 m=100", pair, X, Y, 0, np.full(192, 10.0), 1e-7)
     K = {w: gain_of(mods[w], pair[w], 0.0075) for w in ("ref", "b200")}
     Kf = gain_of(mods["ref"], pair["ref_perm"], 0.0075)
     rep.add("cloth", "LQR seed=0 m=100", "Riccati gain K", relerr(K["b200"], K["ref"]), relerr(Kf, K["ref"]))
@@ -269,6 +314,8 @@ def run_hjb(rep, quick):
         pair = fit_pair(mods, make, X, Y, 0)
         cfg = f"m=100 l=1 gamma={gamma:g}"
         compare_model(rep, "hjb", cfg, pair)
+        if gamma < 1e-4:
+            solver_study(rep, "hjb", cfg, pair, X, Y, 1, [1.0], gamma)
         r = {w: mods[w].validate_dyn_sys(pair[w], traj, ctrl) for w in ("ref", "b200")}
         r_floor = mods["ref"].validate_dyn_sys(pair["ref_perm"], traj, ctrl)
         rep.add("hjb", cfg, "forecast RMSE %", abs(r["b200"] - r["ref"]) / r["ref"], abs(r_floor - r["ref"]) / r["ref"],
@@ -301,6 +348,7 @@ def main():
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "reference_scripts_parity.md"))
     ap.add_argument("--only", default="")
     args = ap.parse_args()
+    import torch  # noqa: F401  (import before the shims: torch inspects every module in sys.modules)
     install_shims()
     rep = Report()
     for name, fn in (("classic", run_classic), ("cloth", run_cloth), ("hjb", run_hjb)):
