@@ -287,214 +287,6 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         self._solve(eng, dev, G, n_total, d)
 
     def lift(self, X):
-        raise NotImplementedError
-
-    def fit(self, X, Y):
-        raise NotImplementedError
-
-    def predict(self, X_aug):
-        """Rows of X_aug are [state | input]; returns (N, n_states) one-step predictions (regressors.py:48-55)."""
-        X_aug = np.asarray(X_aug)
-        n_states = X_aug.shape[1] - self.n_inputs
-        lifted = self.lift(X_aug[:, :n_states].T)
-        return (self.weights @ np.vstack((lifted, X_aug[:, n_states:].T))).T
-
-
-def _engine():
-    from .engine import Engine
-    return Engine.get()
-
-
-def _as_device_rows(eng, a, width=None):
-    """numpy / torch(CPU or CUDA) 2-D -> float64 CUDA tensor with unit column stride (no copy if already there)."""
-    import torch
-    if isinstance(a, torch.Tensor):
-        t = a
-        if t.dtype != torch.float64:
-            t = t.double()
-        if not t.is_cuda:
-            t = t.to(eng.tdev, non_blocking=True)
-        if t.stride(-1) != 1:
-            t = t.contiguous()
-        return t
-    arr = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
-    return torch.from_numpy(arr).to(eng.tdev)
-
-
-class KoopmanNystromRegressor(KoopmanRegressor):
-    """Nystrom-Koopman estimator (regressors.py:114-178) on the B200 kernels.
-
-    fit(X (n, d+p), Y (n, d)) -> None; lift(X (d, N)) -> (m, N); predict(X_aug (N, d+p)) -> (N, d).
-    After fit: A (m,m), B (m,p), C (d,m), weights (d, m+p) are numpy float64; centres are (d, m) like upstream.
-    Additive API: ``forecast`` (batched open-loop rollout), ``fit_distributed`` (sample-sharded fit, one NCCL
-    allreduce of the Grams), ``stream_block`` (rows per host->device block of the streaming fit).
-    """
-
-    stream_block = 262144     # samples per host->device block when inputs live in host memory
-    gram_chunk = 0            # samples per on-chip feature chunk (0: library default 512)
-
-    def __init__(self, n_inputs, kernel=None, gamma=None, m=None):
-        super().__init__(n_inputs, gamma, m)
-        self.kernel = kernel
-        self.nystrom_centers_input = None
-        self.nystrom_centers_output = None
-        self.jitter = 1e-6
-
-    # -- device-side cache (never pickled) ------------------------------------------------------
-    def __getstate__(self):
-        state = dict(self.__dict__)
-        state.pop("_dev", None)
-        return state
-
-    def _device_state(self, n_states):
-        """Landmarks, 1/l, K_zz, S, S^-1 on the device; rebuilt lazily (e.g. after unpickling)."""
-        import torch
-        dev = self.__dict__.get("_dev")
-        Zc = self.nystrom_centers_output
-        if dev is not None and dev["src"] is Zc and dev["kernel"] is self.kernel:
-            return dev
-        eng = _engine()
-        kind, ls = kernel_spec(self.kernel, n_states)
-        Z = torch.from_numpy(np.ascontiguousarray(np.asarray(Zc, dtype=np.float64).T)).to(eng.tdev)   # (m, d) rows
-        inv_ls = torch.from_numpy(1.0 / ls).to(eng.tdev)
-        Kzz = eng.kzz(Z, inv_ls, kind)
-        Kmm = Kzz.clone()
-        Kmm.diagonal().add_(self.jitter)                     # regressors.py:139 (K_mm_out) and :143 (K_mm_in_x)
-        S, Sinv = eng.sym_sqrt(Kmm, lambda_min_bound=self.jitter)
-        dev = dict(src=Zc, kernel=self.kernel, eng=eng, kind=kind, ls=ls, Z=Z, inv_ls=inv_ls, Kzz=Kzz, S=S, Sinv=Sinv)
-        self.__dict__["_dev"] = dev
-        return dev
-
-    # -- landmarks --------------------------------------------------------------------------------
-    def _ensure_centers(self, Y_rows_getter, n):
-        """regressors.py:129-134: one np.random.choice draw on the global legacy RNG, landmarks are next-state
-        samples, input centres alias the output centres; persisted so a refit reuses them."""
-        if self.nystrom_centers_output is None:
-            idx = np.random.choice(np.arange(0, n), size=self.m, replace=False)
-            self.nystrom_centers_output = Y_rows_getter(idx)          # (d, m)
-        if self.nystrom_centers_input is None:
-            self.nystrom_centers_input = self.nystrom_centers_output
-        if self.nystrom_centers_input is not self.nystrom_centers_output and not np.array_equal(
-                self.nystrom_centers_input, self.nystrom_centers_output):
-            raise NotImplementedError("distinct input/output landmark sets are not implemented on the GPU path")
-        self.m = int(np.asarray(self.nystrom_centers_output).shape[1]) if self.m is None else self.m
-
-    @staticmethod
-    def _rows_to_centers(Y, idx):
-        import torch
-        if isinstance(Y, torch.Tensor):
-            sel = Y[torch.as_tensor(idx, device=Y.device, dtype=torch.long)]
-            return np.ascontiguousarray(sel.double().cpu().numpy().T)
-        return np.ascontiguousarray(np.asarray(Y, dtype=np.float64)[idx].T)
-
-    # -- Grams ------------------------------------------------------------------------------------
-    def _accumulate_grams(self, eng, dev, X, Y):
-        """Streams (X, Y) through the fused lift+Gram kernel. Host inputs go up in double-buffered blocks."""
-        import torch
-        n = X.shape[0]
-        eng.gram_begin(dev["Z"], dev["inv_ls"], dev["kind"], self.n_inputs, self.gram_chunk)
-        on_device = isinstance(X, torch.Tensor) and X.is_cuda and isinstance(Y, torch.Tensor) and Y.is_cuda
-        if on_device:
-            Xd, Yd = _as_device_rows(eng, X), _as_device_rows(eng, Y)
-            eng.gram_update(Xd, Yd)
-            return
-        blk = int(self.stream_block)
-        if n <= blk:
-            eng.gram_update(_as_device_rows(eng, X), _as_device_rows(eng, Y))
-            return
-        # double-buffered upload on a side stream, overlapped with the Gram kernel of the previous block
-        Xt = X if isinstance(X, torch.Tensor) else torch.from_numpy(np.asarray(X, dtype=np.float64))
-        Yt = Y if isinstance(Y, torch.Tensor) else torch.from_numpy(np.asarray(Y, dtype=np.float64))
-        wx, wy = Xt.shape[1], Yt.shape[1]
-        bufs = [(torch.empty(blk, wx, dtype=torch.float64, device=eng.tdev), torch.empty(blk, wy, dtype=torch.float64, device=eng.tdev))
-                for _ in range(2)]
-        copy_stream = torch.cuda.Stream(device=eng.tdev)
-        main = torch.cuda.current_stream(eng.tdev)
-        ready = [torch.cuda.Event() for _ in range(2)]
-        freed = [torch.cuda.Event() for _ in range(2)]
-        for b in range(2):
-            freed[b].record(main)
-        nblk = (n + blk - 1) // blk
-        for i in range(nblk):
-            s, e = i * blk, min(n, (i + 1) * blk)
-            b = i & 1
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(freed[b])
-                bufs[b][0][: e - s].copy_(Xt[s:e], non_blocking=True)
-                bufs[b][1][: e - s].copy_(Yt[s:e], non_blocking=True)
-                ready[b].record(copy_stream)
-            main.wait_event(ready[b])
-            eng.gram_update(bufs[b][0][: e - s], bufs[b][1][: e - s])
-            freed[b].record(main)
-        self._h2d_bytes = int(n) * (wx + wy) * 8
-
-    def _solve(self, eng, dev, G, n_total, d):
-        import torch
-        gamma_n = float(self.gamma) * float(n_total)                 # regressors.py:127
-        A, B, C, W = eng.solve_abc(G, dev["Kzz"], dev["S"], dev["Sinv"], gamma_n, self.jitter)
-        dev["W"] = W
-        host = torch.empty(A.numel() + B.numel() + C.numel() + W.numel(), dtype=torch.float64, pin_memory=True)
-        o = 0
-        outs = []
-        for t in (A, B, C, W):
-            host[o:o + t.numel()].copy_(t.reshape(-1), non_blocking=True)
-            outs.append((o, t.shape))
-            o += t.numel()
-        torch.cuda.current_stream(eng.tdev).synchronize()
-        arr = host.numpy()
-        self.A, self.B, self.C, self.weights = (arr[o:o + int(np.prod(s))].reshape(tuple(s)).copy() for o, s in outs)
-        self._d2h_bytes = int(host.numel()) * 8
-
-    # -- public API -------------------------------------------------------------------------------
-    def fit(self, X, Y):
-        """regressors.py:122-169.  X (n, d+p) rows [x_t | u_t], Y (n, d) rows x_{t+1}; numpy, torch CPU (pinned
-        preferred) or torch CUDA.  Returns None like the reference."""
-        n = int(X.shape[0])
-        d = int(X.shape[1]) - self.n_inputs
-        if int(Y.shape[0]) != n or int(Y.shape[1]) != d:
-            raise ValueError("X must be (n, n_states + n_inputs) and Y (n, n_states)")
-        if self.gamma is None or self.kernel is None:
-            raise ValueError("kernel and gamma must be set before fit")
-        self._ensure_centers(lambda idx: self._rows_to_centers(Y, idx), n)
-        dev = self._device_state(d)
-        eng = dev["eng"]
-        self._accumulate_grams(eng, dev, X, Y)
-        G = eng.gram_finalize()
-        self._solve(eng, dev, G, n, d)
-
-    def fit_distributed(self, X_local, Y_local, group=None):
-        """Sample-sharded fit: every rank holds a contiguous block of samples; landmarks are drawn with
-        the reference's call over the GLOBAL sample index (all ranks must share the numpy global RNG state), the
-        local Grams are summed with ONE allreduce, and every rank then solves redundantly (identical results)."""
-        import torch
-        import torch.distributed as dist
-        eng = _engine()
-        n_local = int(X_local.shape[0])
-        d = int(X_local.shape[1]) - self.n_inputs
-        world = dist.get_world_size(group)
-        rank = dist.get_rank(group)
-        counts = torch.zeros(world, dtype=torch.int64, device=eng.tdev)
-        counts[rank] = n_local
-        dist.all_reduce(counts, group=group)
-        offsets = torch.cumsum(counts, 0) - counts
-        n_total, off = int(counts.sum().item()), int(offsets[rank].item())
-        if self.nystrom_centers_output is None:
-            idx = np.random.choice(np.arange(0, n_total), size=self.m, replace=False)
-            Zbuf = torch.zeros(self.m, d, dtype=torch.float64, device=eng.tdev)
-            mine = np.nonzero((idx >= off) & (idx < off + n_local))[0]
-            if mine.size:
-                rows = self._rows_to_centers(Y_local, idx[mine] - off).T          # (k, d)
-                Zbuf[torch.as_tensor(mine, device=eng.tdev)] = torch.from_numpy(np.ascontiguousarray(rows)).to(eng.tdev)
-            dist.all_reduce(Zbuf, group=group)
-            self.nystrom_centers_output = np.ascontiguousarray(Zbuf.cpu().numpy().T)
-        self._ensure_centers(None, n_total)
-        dev = self._device_state(d)
-        self._accumulate_grams(eng, dev, X_local, Y_local)
-        G = eng.gram_finalize()
-        dist.all_reduce(G["_flat"], group=group)                                  # the only data-path collective
-        self._solve(eng, dev, G, n_total, d)
-
-    def lift(self, X):
         """regressors.py:171-178: X (d, N) column-samples -> phi = S^-1 k(Z, X), (m, N).  S^-1 is cached on the
         device (the reference recomputes sqrtm(K_mm) on every call)."""
         import torch
