@@ -106,6 +106,29 @@ int nk_rollout(nk_handle *h, int m, int p, int d, int T, long long nb, const dou
                const double *Z0, const double *U, double *Yhat, const double *Ytrue, double *sq_err, double *sq_sim,
                double *Zfinal, void *stream);
 
+/* ---- cross-validation sweep over the (kernel, gamma) grid: learn_hyperparams in benchmark_lqr_hjb.py:47-71,
+ * benchmark_lqr_classic.py:44-64, benchmark_lqr_cloth.py:39-66 (sklearn GridSearchCV cloning the estimator per candidate and
+ * fold, `fit` on the training fold, score = RMSE of `predict` (regressors.py:48-55) on the held-out fold) ----
+ * nk_cv_weights: for ONE kernel and ONE training fold, all nlam regularisation values at once.  The Grams are the fold's
+ *   (nk_gram_* over the training samples); gamma_n (HOST array, nlam) = gamma * n_train (regressors.py:127).  The nlam
+ *   pairs of regularised systems (regressors.py:151 inner_term, :162 inner_term_rec) are factored as one batch (blocked
+ *   Cholesky batched over the regularisation grid) and solved for the d rows scoring needs:
+ *     Wk[b] (d, m+p) = [ V_phi Kzz Kmm^-1 | V_u ],  V = GYy (gn_b Kmm + Gyy)^-1 [Gyx|Gyu] inner_b^-1,
+ *   so that regressors.py:48-55 reads  Yhat = Wk[b] [k(Z,x); u]   (= weights [S^-1 k(Z,x); u]; the S factors cancel).
+ *   Wk: device (nlam, d, m+p).  info: HOST ints (nlam), 0 ok / 1 inner_term / 2 inner_term_rec / 3 K_mm not SPD.
+ *   The call synchronises the stream.
+ * nk_cv_score: sse[r] += sum_s (Yhat[s, r] - Y[s, r % d])^2 for the R = nlam*d stacked weight rows Wk (R, m+p) over
+ *   the N held-out samples X_aug (N, d+p), Y (N, d).  sse (R) device, caller-zeroed (accumulates across calls).
+ *   sklearn's 'neg_root_mean_squared_error' for value b is  -mean_j sqrt(sse[b*d + j] / N).
+ * nk_axpy: y += alpha x (count doubles) -- combines per-fold Grams into training-fold Grams on the device. */
+int nk_cv_weights(nk_handle *h, int m, int p, int d, int nlam, const double *gamma_n, double jitter,
+                  const double *Gxx, const double *Gyx, const double *Gyy, const double *Gxu, const double *Gyu,
+                  const double *Guu, const double *GYy, const double *Kzz, double *Wk, int *info, void *stream);
+int nk_cv_score(nk_handle *h, const double *Z, long long ldz, int m, int d, int p, const double *inv_ls, int kind,
+                const double *Wk, int R, const double *X_aug, long long ldx, const double *Y, long long ldy, long long N,
+                double *sse, void *stream);
+int nk_axpy(nk_handle *h, long long count, double alpha, const double *x, double *y, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,14 +32,7 @@ void launch_pack_landmarks(const double *Z, long long ldz, int m, int d, int MP,
 void launch_unpack(const double *Gws, const int *tile_of, int nblk, int row0, int col0, int rows, int cols,
                    double *out, long long ld, int accumulate, cudaStream_t stream);
 
-// centre = mean of the landmarks: shrinks |x'|^2 + |z'|^2 in the norm expansion (distances are shift invariant)
-__global__ void landmark_center_kernel(const double *Z, long long ldz, int m, int d, double *center) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= d) return;
-    double s = 0.0;
-    for (int r = 0; r < m; r++) s += Z[(long long)r * ldz + k];
-    center[k] = s / m;
-}
+void landmark_center(const double *Z, long long ldz, int m, int d, double *center, cudaStream_t stream);   // nk_dense.cu
 
 // register-only DMMA issue-rate probe: 32 independent accumulator tiles per warp, 8 warps per CTA, 2 CTAs per SM
 __global__ void __launch_bounds__(256) dmma_probe_kernel(double *out, int iters, double a0, double b0) {
@@ -200,7 +193,7 @@ int nk_gram_begin(nk_handle *h, const double *Z, long long ldz, int m, int d, in
     NK_CUDA(h, cudaMemcpyAsync(h->tile_of.ptr, h->h_tile_of.data(), h->h_tile_of.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
     NK_CUDA(h, cudaStreamSynchronize(stream));   // `period` and h_tile_of staging are host temporaries
     NK_CUDA(h, cudaMemcpyAsync(h->inv_ls.ptr, inv_ls, (size_t)d * 8, cudaMemcpyDeviceToDevice, stream));
-    landmark_center_kernel<<<(d + 127) / 128, 128, 0, stream>>>(Z, ldz, m, d, (double *)h->center.ptr);
+    landmark_center(Z, ldz, m, d, (double *)h->center.ptr, stream);
     launch_pack_landmarks(Z, ldz, m, d, h->MP, h->KLS, (const double *)h->inv_ls.ptr, (const double *)h->center.ptr,
                           (double *)h->zp.ptr, stream);
     NK_CUDA(h, cudaMemsetAsync(h->gws.ptr, 0, (size_t)h->ntiles * kTile * kTile * 8, stream));

@@ -28,6 +28,7 @@ struct GemmArgs {
     double *C; long long ldc;
     double *Ct; long long ldct;
     int flags, epi_kind, tiles_n;
+    long long sA, sB, sC, sCt;   // batch strides (elements); blockIdx.y = batch index
 };
 
 __device__ __forceinline__ void cp_async16(void *dst, const void *src, int bytes) {
@@ -87,10 +88,16 @@ __device__ __forceinline__ void warp_mma_slab_d(double (&acc)[8][4][2], const do
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(256, 1) gemm_nt_kernel(const GemmArgs g) {
+__global__ void __launch_bounds__(256, 1) gemm_nt_kernel(GemmArgs g) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     double *sm = reinterpret_cast<double *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    {
+        const long long bz = blockIdx.y;
+        g.A += bz * g.sA; g.B += bz * g.sB;
+        if (g.C) g.C += bz * g.sC;
+        if (g.Ct) g.Ct += bz * g.sCt;
+    }
     int I, J;
     if (g.flags & kGemmLowerOnly) {
         // blockIdx.x enumerates the lower triangle row by row
@@ -167,7 +174,13 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_kernel(const GemmArgs g) {
 void gemm_nt(nk_handle *h, int M, int N, int K, double alpha, const double *A, long long lda, const double *B, long long ldb,
              double beta, double *C, long long ldc, double diag, int flags, double *Ct, long long ldct, cudaStream_t stream,
              int epi_kind) {
-    if (M <= 0 || N <= 0) return;
+    gemm_nt_batched(h, 1, M, N, K, alpha, A, lda, 0, B, ldb, 0, beta, C, ldc, 0, diag, flags, Ct, ldct, 0, stream, epi_kind);
+}
+
+void gemm_nt_batched(nk_handle *h, int batch, int M, int N, int K, double alpha, const double *A, long long lda, long long sA,
+                     const double *B, long long ldb, long long sB, double beta, double *C, long long ldc, long long sC, double diag,
+                     int flags, double *Ct, long long ldct, long long sCt, cudaStream_t stream, int epi_kind) {
+    if (M <= 0 || N <= 0 || batch <= 0) return;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
@@ -178,12 +191,14 @@ void gemm_nt(nk_handle *h, int M, int N, int K, double alpha, const double *A, l
     g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.diag = diag;
     g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc; g.Ct = Ct; g.ldct = ldct;
     g.flags = flags; g.epi_kind = epi_kind;
+    g.sA = sA; g.sB = sB; g.sC = sC; g.sCt = sCt;
     const int tm = (M + kTile - 1) / kTile, tn = (N + kTile - 1) / kTile;
     g.tiles_n = tn;
     const int grid = (flags & kGemmLowerOnly) ? tm * (tm + 1) / 2 : tm * tn;
-    const bool vec2 = ((lda | ldb) % 2 == 0) && (((uintptr_t)A | (uintptr_t)B) % 16 == 0);
-    if (vec2) gemm_nt_kernel<2><<<grid, 256, kGemmSmem, stream>>>(g);
-    else gemm_nt_kernel<1><<<grid, 256, kGemmSmem, stream>>>(g);
+    const bool vec2 = ((lda | ldb | sA | sB) % 2 == 0) && (((uintptr_t)A | (uintptr_t)B) % 16 == 0);
+    const dim3 grid2(grid, batch);
+    if (vec2) gemm_nt_kernel<2><<<grid2, 256, kGemmSmem, stream>>>(g);
+    else gemm_nt_kernel<1><<<grid2, 256, kGemmSmem, stream>>>(g);
     h->launches++;
 }
 
@@ -220,8 +235,9 @@ __global__ void scale_copy_kernel(int rows, int cols, double scale, const double
     const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
     if (c < cols) dst[(long long)r * ldd + c] = scale * src[(long long)r * lds + c];
 }
-__global__ void zero_upper_kernel(int n, double *A, long long lda) {
+__global__ void zero_upper_kernel(int n, double *A, long long lda, long long sA) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    A += (long long)blockIdx.z * sA;
     if (c < n && c > r) A[(long long)r * lda + c] = 0.0;
 }
 __global__ void rowsum_max_kernel(int n, const double *A, long long lda, double *out) {
@@ -237,15 +253,23 @@ __global__ void rowsum_max_kernel(int n, const double *A, long long lda, double 
 }
 static void launch2d(int rows, int cols, dim3 &grid, dim3 &block) { block = dim3(128); grid = dim3((cols + 127) / 128, rows); }
 
+// centre = column means of the landmarks (any shift is valid: distances are shift invariant; the mean minimises the norms
+// entering the expansion).  32 columns x 32 row lanes per CTA, fixed-order tree over the row lanes -> deterministic.
 __global__ void landmark_center_kernel2(const double *Z, long long ldz, int m, int d, double *center) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= d) return;
+    __shared__ double part[32][33];
+    const int k = blockIdx.x * 32 + threadIdx.x;
     double s = 0.0;
-    for (int r = 0; r < m; r++) s += Z[(long long)r * ldz + k];
-    center[k] = s / m;
+    if (k < d) for (int r = threadIdx.y; r < m; r += 32) s += Z[(long long)r * ldz + k];
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && k < d) {
+        double t = 0.0;
+        for (int j = 0; j < 32; j++) t += part[j][threadIdx.x];
+        center[k] = t / m;
+    }
 }
 void landmark_center(const double *Z, long long ldz, int m, int d, double *center, cudaStream_t stream) {
-    landmark_center_kernel2<<<(d + 127) / 128, 128, 0, stream>>>(Z, ldz, m, d, center);
+    landmark_center_kernel2<<<(d + 31) / 32, dim3(32, 32), 0, stream>>>(Z, ldz, m, d, center);
 }
 
 __global__ void augment_rows_kernel(const double *src, long long lds, long long rows, int d, const double *inv_ls, const double *center,
@@ -275,97 +299,215 @@ void augment_rows(nk_handle *h, const double *src, long long lds, long long rows
 }
 
 // ---------------------------------------------------------------------------------------------------
-// 128 x 128 diagonal block: Cholesky + inverse of the factor, one CTA
+// 128 x 128 diagonal block: Cholesky factor and its inverse, one CTA of 256 threads per matrix of the batch.
+//
+// Register-tiled and cyclic: thread (ty, tx) = (tid / 16, tid % 16) owns the 64 elements (ty + 16 i, tx + 16 j).
+// Pass 1 (right-looking Cholesky): per pivot k the owners of column k publish it through a double-buffered
+// shared vector (ONE barrier per pivot); every thread scales it with rsqrt(a_kk) and applies the rank-1 update to
+// the lower-triangular part of its registers.  Pass 2 (Gauss-Jordan on the identity): L^-1 by forward elimination
+// with the columns of L kept in shared memory.  Loops are unrolled over the 16-wide register block index so that
+// every register access is static.  Blocks smaller than 128 are padded with the identity.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kDB = 128, kDBld = 129;
-__global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double *A, long long lda, int nb, int j0, double *dinv, double *dinvT, int *info, int do_factor) {
-    extern __shared__ double Ls[];   // kDB x kDBld
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < kDB * kDB; idx += 256) {
-        const int r = idx / kDB, c = idx % kDB;
-        double v = (r == c) ? 1.0 : 0.0;
-        if (r < nb && c < nb) v = (c <= r) ? A[(long long)r * lda + c] : 0.0;
-        Ls[r * kDBld + c] = v;
-    }
-    __syncthreads();
-    // right-looking Cholesky on the lower triangle (skipped when the block already holds a factor)
-    for (int k = 0; k < (do_factor ? nb : 0); k++) {
-        const double akk = Ls[k * kDBld + k];
-        double piv;
-        if (!(akk > 0.0)) { piv = 1.0; if (tid == 0) atomicCAS(info, 0, j0 + k + 1); }
-        else piv = sqrt(akk);
-        __syncthreads();
-        if (tid == 0) Ls[k * kDBld + k] = piv;
-        for (int i = k + 1 + tid; i < nb; i += 256) Ls[i * kDBld + k] /= piv;
-        __syncthreads();
-        // trailing update of rows i > k, columns k < j <= i
-        const int rem = nb - k - 1;
-        for (int idx = tid; idx < rem * rem; idx += 256) {
-            const int i = k + 1 + idx / rem, j = k + 1 + idx % rem;
-            if (j <= i) Ls[i * kDBld + j] -= Ls[i * kDBld + k] * Ls[j * kDBld + k];
+constexpr int kDB = 128;
+constexpr size_t kDiagSmem = (size_t)kDB * kDB * 8 + 2 * kDB * 8 + 2 * kDB * 8 + kDB * 8;
+
+__global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double *A_, long long lda, long long strideA, int nb, int j0, double *dinv_,
+                                                            double *dinvT_, long long strideD, int *info_, int do_factor) {
+    extern __shared__ __align__(16) double dsm[];
+    double *Lc = dsm;                       // Lc[k * 128 + r] = L(r, k), r > k
+    double *colb = Lc + kDB * kDB;          // 2 x 128: published pivot column / row
+    double *invd = colb + 2 * kDB;          // 1 / L(k, k)
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    double *A = A_ + (long long)blockIdx.x * strideA;
+    double *dinv = dinv_ + (long long)blockIdx.x * strideD;
+    double *dinvT = dinvT_ ? dinvT_ + (long long)blockIdx.x * strideD : nullptr;
+    int *info = info_ + blockIdx.x;
+
+    double a[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int r = ty + 16 * i, c = tx + 16 * j;
+            double v = (r == c) ? 1.0 : 0.0;
+            if (r < nb && c < nb) v = (c <= r) ? A[(long long)r * lda + c] : 0.0;
+            a[i][j] = v;
         }
-        __syncthreads();
-    }
-    // write L (and zero the strict upper part of the block)
-    for (int idx = tid; idx < (do_factor ? nb * nb : 0); idx += 256) {
-        const int r = idx / nb, c = idx % nb;
-        A[(long long)r * lda + c] = (c <= r) ? Ls[r * kDBld + c] : 0.0;
-    }
-    __syncthreads();
-    // inverse: thread j solves L x = e_j; x_i (i > j) is parked in the unused upper triangle at Ls[j][i]
-    if (tid < kDB) {
-        const int j = tid;
-        const double xjj = 1.0 / Ls[j * kDBld + j];
-        for (int i = j + 1; i < kDB; i++) {
-            double s0 = Ls[i * kDBld + j] * xjj, s1 = 0.0;
-            int k = j + 1;
-            for (; k + 1 < i; k += 2) {
-                s0 += Ls[i * kDBld + k] * Ls[j * kDBld + k];
-                s1 += Ls[i * kDBld + k + 1] * Ls[j * kDBld + k + 1];
+    if (do_factor) {
+#pragma unroll
+        for (int kq = 0; kq < 8; kq++) {
+            for (int kr = 0; kr < 16; kr++) {
+                const int k = kq * 16 + kr;
+                if (k >= nb) break;
+                double *buf = colb + (k & 1) * kDB;
+                if (tx == kr) {
+#pragma unroll
+                    for (int i = kq; i < 8; i++) buf[ty + 16 * i] = a[i][kq];
+                }
+                __syncthreads();
+                double akk = buf[k];
+                if (!(akk > 0.0)) { if (tid == 0) atomicCAS(info, 0, j0 + k + 1); akk = 1.0; }
+                const double inv = rsqrt(akk);
+                double lr[8], lc[8];
+#pragma unroll
+                for (int i = kq; i < 8; i++) lr[i] = (ty + 16 * i > k) ? buf[ty + 16 * i] * inv : 0.0;
+#pragma unroll
+                for (int j = kq; j < 8; j++) lc[j] = (tx + 16 * j > k) ? buf[tx + 16 * j] * inv : 0.0;
+#pragma unroll
+                for (int i = kq; i < 8; i++)
+#pragma unroll
+                    for (int j = kq; j <= i; j++) a[i][j] -= lr[i] * lc[j];
+                if (tx == kr) {
+#pragma unroll
+                    for (int i = kq; i < 8; i++) {
+                        const int r = ty + 16 * i;
+                        if (r > k) { a[i][kq] = lr[i]; Lc[k * kDB + r] = lr[i]; }
+                        else if (r == k) { a[i][kq] = akk * inv; invd[k] = inv; }
+                    }
+                }
             }
-            if (k < i) s0 += Ls[i * kDBld + k] * Ls[j * kDBld + k];
-            Ls[j * kDBld + i] = -(s0 + s1) / Ls[i * kDBld + i];
         }
+        // identity padding of a short block
+        for (int k = nb + tid; k < kDB; k += 256) invd[k] = 1.0;
+        for (int idx = tid; idx < (kDB - nb) * kDB; idx += 256) Lc[(nb + idx / kDB) * kDB + idx % kDB] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int r = ty + 16 * i, c = tx + 16 * j;
+                if (r < nb && c < nb) A[(long long)r * lda + c] = (c <= r) ? a[i][j] : 0.0;
+            }
+    } else {
+        // the block already holds a factor: publish its columns for pass 2
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int r = ty + 16 * i, c = tx + 16 * j;
+                if (c < r) Lc[c * kDB + r] = a[i][j];
+                else if (c == r) invd[r] = 1.0 / a[i][j];
+            }
     }
     __syncthreads();
-    for (int idx = tid; idx < kDB * kDB; idx += 256) {
-        const int r = idx / kDB, c = idx % kDB;   // Linv(r,c), r >= c
-        double v = 0.0;
-        if (c < r) v = Ls[c * kDBld + r];
-        else if (c == r) v = 1.0 / Ls[r * kDBld + r];
-        dinv[idx] = v;
-        dinvT[c * kDB + r] = v;
+
+    // ---- pass 2: X = L^-1 by forward elimination of the identity ----
+    double x[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) x[i][j] = (ty + 16 * i == tx + 16 * j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int kq = 0; kq < 8; kq++) {
+        for (int kr = 0; kr < 16; kr++) {
+            const int k = kq * 16 + kr;
+            double *buf = colb + (k & 1) * kDB;
+            if (ty == kr) {
+#pragma unroll
+                for (int j = 0; j <= kq; j++) buf[tx + 16 * j] = x[kq][j];
+            }
+            __syncthreads();
+            const double dk = invd[k];
+            double xr[8], lk[8];
+#pragma unroll
+            for (int j = 0; j <= kq; j++) xr[j] = (tx + 16 * j <= k) ? buf[tx + 16 * j] * dk : 0.0;
+#pragma unroll
+            for (int i = kq; i < 8; i++) lk[i] = (ty + 16 * i > k) ? Lc[k * kDB + ty + 16 * i] : 0.0;
+#pragma unroll
+            for (int i = kq; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j <= kq; j++) x[i][j] -= lk[i] * xr[j];
+            if (ty == kr) {
+#pragma unroll
+                for (int j = 0; j <= kq; j++) x[kq][j] = xr[j];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int r = ty + 16 * i, c = tx + 16 * j;
+            const double v = (c <= r) ? x[i][j] : 0.0;
+            dinv[r * kDB + c] = v;
+        }
+    if (dinvT) {
+        // transposed copy with coalesced stores: thread owns (r, c) -> write element (c, r) of L^-1 ... via shared staging
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int r = ty + 16 * i, c = tx + 16 * j;
+                Lc[c * kDB + r] = (c <= r) ? x[i][j] : 0.0;      // Lc[c][r] = X(r, c) = X^T(c, r)
+            }
+        __syncthreads();
+        for (int idx = tid; idx < kDB * kDB; idx += 256) dinvT[idx] = Lc[idx];
     }
 }
 
-int potrf_blocked(nk_handle *h, int n, double *A, long long lda, double *Lt, long long ldlt, double *dinv, double *dinvT,
-                  int *dinfo, cudaStream_t stream) {
+static void launch_diag(nk_handle *h, int batch, double *A, long long lda, long long sA, int nb, int j0, double *dinv, double *dinvT,
+                        long long sD, int *dinfo, int do_factor, cudaStream_t stream) {
     static bool configured = false;
-    const size_t smem = (size_t)kDB * kDBld * 8;
-    if (!configured) { cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
-    cudaMemsetAsync(dinfo, 0, sizeof(int), stream);
+    if (!configured) { cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem); configured = true; }
+    potrf_diag_kernel<<<batch, 256, kDiagSmem, stream>>>(A, lda, sA, nb, j0, dinv, dinvT, sD, dinfo, do_factor);
+    h->launches++;
+}
+
+__global__ void transpose_batched_kernel(int rows, int cols, const double *src, long long lds, long long ss, double *dst, long long ldd, long long sd) {
+    __shared__ double tile[32][33];
+    src += (long long)blockIdx.z * ss; dst += (long long)blockIdx.z * sd;
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int r = by + j, c = bx + threadIdx.x;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = src[(long long)r * lds + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c = bx + j, r = by + threadIdx.x;
+        if (r < rows && c < cols) dst[(long long)c * ldd + r] = tile[threadIdx.x][j];
+    }
+}
+void transpose_batched(nk_handle *h, int batch, int rows, int cols, const double *src, long long lds, long long ss, double *dst,
+                       long long ldd, long long sd, cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0 || batch <= 0) return;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch), block(32, 8);
+    transpose_batched_kernel<<<grid, block, 0, stream>>>(rows, cols, src, lds, ss, dst, ldd, sd);
+    h->launches++;
+}
+
+// Batched blocked Cholesky (right-looking, 128-wide panels): every matrix of the batch advances through the same
+// launches (grid.y / grid.x = batch), so the serial diagonal-block kernel of one matrix overlaps with the others'.
+// dinfo: `batch` device ints (0 or the 1-based index of the first non-positive pivot).
+int potrf_batched(nk_handle *h, int batch, int n, double *A, long long lda, long long sA, double *Lt, long long ldlt, long long sLt,
+                  double *dinv, double *dinvT, long long sD, int *dinfo, cudaStream_t stream) {
+    cudaMemsetAsync(dinfo, 0, sizeof(int) * batch, stream);
     const int nblk = (n + kDB - 1) / kDB;
     for (int kb = 0; kb < nblk; kb++) {
         const int j0 = kb * kDB, nb = (n - j0 < kDB) ? n - j0 : kDB, rem = n - j0 - nb;
         double *Akk = A + (long long)j0 * lda + j0;
         double *di = dinv + (size_t)kb * kDB * kDB;
-        potrf_diag_kernel<<<1, 256, smem, stream>>>(Akk, lda, nb, j0, di, dinvT + (size_t)kb * kDB * kDB, dinfo, 1);
-        h->launches++;
+        launch_diag(h, batch, Akk, lda, sA, nb, j0, di, dinvT ? dinvT + (size_t)kb * kDB * kDB : nullptr, sD, dinfo, 1, stream);
         if (rem > 0) {
             double *A21 = A + (long long)(j0 + nb) * lda + j0;
-            gemm_nt(h, rem, nb, nb, 1.0, A21, lda, di, kDB, 0.0, A21, lda, 0.0, 0, nullptr, 0, stream);
+            gemm_nt_batched(h, batch, rem, nb, nb, 1.0, A21, lda, sA, di, kDB, sD, 0.0, A21, lda, sA, 0.0, 0, nullptr, 0, 0, stream);
             double *A22 = A + (long long)(j0 + nb) * lda + (j0 + nb);
-            gemm_nt(h, rem, rem, nb, -1.0, A21, lda, A21, lda, 1.0, A22, lda, 0.0, kGemmLowerOnly, nullptr, 0, stream);
+            gemm_nt_batched(h, batch, rem, rem, nb, -1.0, A21, lda, sA, A21, lda, sA, 1.0, A22, lda, sA, 0.0, kGemmLowerOnly, nullptr, 0, 0, stream);
         }
     }
-    dim3 grid, block;
-    launch2d(n, n, grid, block);
-    zero_upper_kernel<<<grid, block, 0, stream>>>(n, A, lda);
+    dim3 block(128), grid((n + 127) / 128, n, batch);
+    zero_upper_kernel<<<grid, block, 0, stream>>>(n, A, lda, sA);
     h->launches++;
-    if (Lt) transpose(h, n, n, A, lda, Lt, ldlt, stream);
+    if (Lt) transpose_batched(h, batch, n, n, A, lda, sA, Lt, ldlt, sLt, stream);
     return NK_OK;
 }
 
+int potrf_blocked(nk_handle *h, int n, double *A, long long lda, double *Lt, long long ldlt, double *dinv, double *dinvT,
+                  int *dinfo, cudaStream_t stream) {
+    return potrf_batched(h, 1, n, A, lda, 0, Lt, ldlt, 0, dinv, dinvT, 0, dinfo, stream);
+}
+
+// ---- triangular solves in transposed storage (Xt rows = right-hand sides) ----
+// left-looking (gathers; r large):  block i of the unknown is a product over all earlier blocks
 void trsm_fwd_t(nk_handle *h, int n, int r, const double *L, long long ldl, const double *dinv, double *Xt, long long ldx, cudaStream_t stream) {
     const int nblk = (n + kDB - 1) / kDB;
     for (int i = 0; i < nblk; i++) {
@@ -380,6 +522,28 @@ void trsm_bwd_t(nk_handle *h, int n, int r, const double *Lt, long long ldlt, co
         const int j0 = i * kDB, nb = (n - j0 < kDB) ? n - j0 : kDB, j1 = j0 + nb;
         if (j1 < n) gemm_nt(h, r, nb, n - j1, -1.0, Xt + j1, ldx, Lt + (long long)j0 * ldlt + j1, ldlt, 1.0, Xt + j0, ldx, 0.0, 0, nullptr, 0, stream);
         gemm_nt(h, r, nb, nb, 1.0, Xt + j0, ldx, dinvT + (size_t)i * kDB * kDB, kDB, 0.0, Xt + j0, ldx, 0.0, 0, nullptr, 0, stream);
+    }
+}
+// right-looking, batched (scatters; few right-hand sides): once block i of the unknown is known, all later
+// (forward) / earlier (backward) blocks are updated by one wide product -> (n / 128) CTAs per launch even when r is small.
+// sL / sD / sX = 0 shares the factor / right-hand sides across the batch.
+void trsm_fwd_t_rl(nk_handle *h, int batch, int n, int r, const double *L, long long ldl, long long sL, const double *dinv, long long sD,
+                   double *Xt, long long ldx, long long sX, cudaStream_t stream) {
+    const int nblk = (n + kDB - 1) / kDB;
+    for (int i = 0; i < nblk; i++) {
+        const int j0 = i * kDB, nb = (n - j0 < kDB) ? n - j0 : kDB, j1 = j0 + nb;
+        gemm_nt_batched(h, batch, r, nb, nb, 1.0, Xt + j0, ldx, sX, dinv + (size_t)i * kDB * kDB, kDB, sD, 0.0, Xt + j0, ldx, sX, 0.0, 0, nullptr, 0, 0, stream);
+        if (j1 < n) gemm_nt_batched(h, batch, r, n - j1, nb, -1.0, Xt + j0, ldx, sX, L + (long long)j1 * ldl + j0, ldl, sL, 1.0, Xt + j1, ldx, sX,
+                                    0.0, 0, nullptr, 0, 0, stream);
+    }
+}
+void trsm_bwd_t_rl(nk_handle *h, int batch, int n, int r, const double *Lt, long long ldlt, long long sLt, const double *dinvT, long long sD,
+                   double *Xt, long long ldx, long long sX, cudaStream_t stream) {
+    const int nblk = (n + kDB - 1) / kDB;
+    for (int i = nblk - 1; i >= 0; i--) {
+        const int j0 = i * kDB, nb = (n - j0 < kDB) ? n - j0 : kDB;
+        gemm_nt_batched(h, batch, r, nb, nb, 1.0, Xt + j0, ldx, sX, dinvT + (size_t)i * kDB * kDB, kDB, sD, 0.0, Xt + j0, ldx, sX, 0.0, 0, nullptr, 0, 0, stream);
+        if (j0 > 0) gemm_nt_batched(h, batch, r, j0, nb, -1.0, Xt + j0, ldx, sX, Lt + j0, ldlt, sLt, 1.0, Xt, ldx, sX, 0.0, 0, nullptr, 0, 0, stream);
     }
 }
 
@@ -466,16 +630,13 @@ int nk_trsm_lower(nk_handle *h, int trans, int n, int nrhs, const double *L, lon
     if ((rc = ensure(h, h->dinfo, 64)) != NK_OK) return rc;
     NK_CUDA(h, cudaMemcpy2DAsync(Lc, ldn * 8, L, ldl * 8, (size_t)n * 8, n, cudaMemcpyDeviceToDevice, stream));
     // diagonal-block inverses straight from the given factor (do_factor = 0)
-    const size_t smem = (size_t)kDB * kDBld * 8;
-    cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int i = 0; i < nblk; i++) {
         const int j0 = i * kDB, nb = (n - j0 < kDB) ? n - j0 : kDB;
-        potrf_diag_kernel<<<1, 256, smem, stream>>>(Lc + (long long)j0 * ldn + j0, ldn, nb, j0, dinv + (size_t)i * kDB * kDB,
-                                                    dinvT + (size_t)i * kDB * kDB, (int *)h->dinfo.ptr, 0);
-        h->launches++;
+        launch_diag(h, 1, Lc + (long long)j0 * ldn + j0, ldn, 0, nb, j0, dinv + (size_t)i * kDB * kDB, dinvT + (size_t)i * kDB * kDB, 0,
+                    (int *)h->dinfo.ptr, 0, stream);
     }
     dim3 grid, block; launch2d(n, n, grid, block);
-    zero_upper_kernel<<<grid, block, 0, stream>>>(n, Lc, ldn);
+    zero_upper_kernel<<<grid, block, 0, stream>>>(n, Lc, ldn, 0);
     transpose(h, n, n, Lc, ldn, Lt, ldn, stream);
     transpose(h, n, nrhs, B, ldb, Xt, ldn, stream);
     if (!trans) trsm_fwd_t(h, n, nrhs, Lc, ldn, dinv, Xt, ldn, stream);

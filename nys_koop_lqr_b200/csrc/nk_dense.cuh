@@ -18,12 +18,26 @@ void gemm_nt(nk_handle *h, int M, int N, int K, double alpha, const double *A, l
              double beta, double *C, long long ldc, double diag, int flags, double *Ct, long long ldct, cudaStream_t stream,
              int epi_kind = -1);
 
+void gemm_nt_batched(nk_handle *h, int batch, int M, int N, int K, double alpha, const double *A, long long lda, long long sA,
+                     const double *B, long long ldb, long long sB, double beta, double *C, long long ldc, long long sC, double diag,
+                     int flags, double *Ct, long long ldct, long long sCt, cudaStream_t stream, int epi_kind = -1);
+
+void transpose_batched(nk_handle *h, int batch, int rows, int cols, const double *src, long long lds, long long ss, double *dst,
+                       long long ldd, long long sd, cudaStream_t stream);
 void transpose(nk_handle *h, int rows, int cols, const double *src, long long lds, double *dst, long long ldd, cudaStream_t stream);
 
 // Cholesky of the n x n SPD matrix in A (lower), in place; Lt (n,n) receives L^T (upper, row-major); inverses of the
 // 128x128 diagonal blocks go to dinv (nblk x 128 x 128, row-major L_ii^-1) and dinvT (their transposes).  dinfo: device int.
 int potrf_blocked(nk_handle *h, int n, double *A, long long lda, double *Lt, long long ldlt, double *dinv, double *dinvT,
                   int *dinfo, cudaStream_t stream);
+// batched form: matrix b lives at A + b*sA (Lt + b*sLt, dinv + b*sD, ...); dinfo holds `batch` device ints
+int potrf_batched(nk_handle *h, int batch, int n, double *A, long long lda, long long sA, double *Lt, long long ldlt, long long sLt,
+                  double *dinv, double *dinvT, long long sD, int *dinfo, cudaStream_t stream);
+// right-looking batched triangular solves for few right-hand sides (stride 0 = shared across the batch)
+void trsm_fwd_t_rl(nk_handle *h, int batch, int n, int r, const double *L, long long ldl, long long sL, const double *dinv, long long sD,
+                   double *Xt, long long ldx, long long sX, cudaStream_t stream);
+void trsm_bwd_t_rl(nk_handle *h, int batch, int n, int r, const double *Lt, long long ldlt, long long sLt, const double *dinvT, long long sD,
+                   double *Xt, long long ldx, long long sX, cudaStream_t stream);
 // transposed-storage triangular solves with the factor above.  Xt (r, n) row-major holds B^T on entry.
 //   forward : Xt <- Xt L^-T   (i.e. X = L^-1 B)        backward: Xt <- Xt L^-1   (i.e. X = L^-T B)
 void trsm_fwd_t(nk_handle *h, int n, int r, const double *L, long long ldl, const double *dinv, double *Xt, long long ldx, cudaStream_t stream);

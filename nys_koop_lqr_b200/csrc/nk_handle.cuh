@@ -27,7 +27,7 @@ struct nk_handle {
     std::vector<int> h_tile_of;
 
     // ---- dense-stage scratch (grow-only), see nk_dense.cu ----
-    nk_devbuf dense[12];
+    nk_devbuf dense[16];
     nk_devbuf dinfo;
 };
 

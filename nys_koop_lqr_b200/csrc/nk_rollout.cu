@@ -27,13 +27,23 @@ __global__ void step_error_kernel(long long nb, int d, const double *Yh, const d
 }
 
 __global__ void copy_cols_kernel(long long rows, int cols, const double *src, long long lds, double *dst, long long ldd) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const long long r = blockIdx.y;
-    if (c < cols && r < rows) dst[r * ldd + c] = src[r * lds + c];
+    const long long total = rows * cols;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / cols;
+        const int c = (int)(idx % cols);
+        dst[r * ldd + c] = src[r * lds + c];
+    }
+}
+void copy_cols(nk_handle *h, long long rows, int cols, const double *src, long long lds, double *dst, long long ldd, cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0) return;
+    const long long total = rows * cols;
+    const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    copy_cols_kernel<<<blocks, 256, 0, stream>>>(rows, cols, src, lds, dst, ldd);
+    h->launches++;
 }
 
 // K^T = k(X, Z): (N, m), rows = points
-static int kernel_cross_t(nk_handle *h, const double *Z, long long ldz, int m, int d, const double *inv_ls, int kind,
+int kernel_cross_t(nk_handle *h, const double *Z, long long ldz, int m, int d, const double *inv_ls, int kind,
                           const double *X, long long ldx, long long N, double *Kt, long long ldkt, cudaStream_t stream) {
     int rc;
     const int KA = even_i(d + 2);
@@ -88,11 +98,7 @@ int nk_predict(nk_handle *h, const double *Z, long long ldz, int m, int d, int p
     double *F = dense_scratch(h, 3, (size_t)N * ldf, &rc); if (rc) return rc;    // [Phi^T | U] (N, m+p)
     if ((rc = kernel_cross_t(h, Z, ldz, m, d, inv_ls, kind, X_aug, ldx, N, Kt, ldm, stream)) != NK_OK) return rc;
     gemm_nt(h, (int)N, m, m, 1.0, Kt, ldm, Sinv, ldsi, 0.0, F, ldf, 0.0, 0, nullptr, 0, stream);
-    if (p) {
-        dim3 block(32), grid((p + 31) / 32, (unsigned)N);
-        copy_cols_kernel<<<grid, block, 0, stream>>>(N, p, X_aug + d, ldx, F + m, ldf);
-        h->launches++;
-    }
+    copy_cols(h, N, p, X_aug + d, ldx, F + m, ldf, stream);
     gemm_nt(h, (int)N, d, m + p, 1.0, F, ldf, W, ldw, 0.0, Yhat, ldy, 0.0, 0, nullptr, 0, stream);
     NK_CUDA(h, cudaGetLastError());
     return NK_OK;

@@ -125,6 +125,16 @@ class Engine:
         self._ck(self.lib.nk_gram_finalize(self.h, *args, int(bool(accumulate)), self._stream()), "nk_gram_finalize")
         return out
 
+    def gram_views(self, flat, m, d, p):
+        """Named views of a packed Gram buffer [Gxx|Gyx|Gyy|Gxu|Gyu|Guu|GYy] (the layout gram_finalize allocates)."""
+        sizes = dict(Gxx=(m, m), Gyx=(m, m), Gyy=(m, m), Gxu=(m, p), Gyu=(m, p), Guu=(p, p), GYy=(d, m))
+        out = {"_flat": flat}
+        o = 0
+        for k, (a, b) in sizes.items():
+            out[k] = flat[o:o + a * b].view(a, b)
+            o += a * b
+        return out
+
     def grams(self, X_aug, Y, Z, inv_ls, kind, p, chunk=0):
         self.gram_begin(Z, inv_ls, kind, p, chunk)
         self.gram_update(X_aug, Y)
@@ -198,6 +208,43 @@ class Engine:
                                        _ptr(_f64(S, "S")), _ptr(_f64(Sinv, "Sinv")), _ptr(A), _ptr(B) if p else C.c_void_p(0),
                                        _ptr(Cm), _ptr(W), C.byref(info), self._stream()), "nk_solve_abc")
         return A, B, Cm, W
+
+    # ------------------------------------------------------------------ cross-validation sweep
+    def axpy(self, alpha, x, y):
+        """y += alpha * x on the device (flat float64 buffers of equal length)."""
+        _f64(x, "x"); _f64(y, "y")
+        if x.numel() != y.numel():
+            raise ValueError("axpy: length mismatch")
+        self._ck(self.lib.nk_axpy(self.h, x.numel(), float(alpha), _ptr(x), _ptr(y), self._stream()), "nk_axpy")
+        return y
+
+    def cv_weights(self, G, Kzz, gamma_n, jitter=JITTER):
+        """All regularisation values of one (kernel, training fold) as one batch.  gamma_n: sequence of gamma * n_train.
+        Returns (Wk (nlam, d, m+p) prediction weights in kernel-matrix coordinates, info list: 0 ok / 1,2,3 not SPD)."""
+        m = Kzz.shape[0]
+        p = G["Guu"].shape[0]
+        d = G["GYy"].shape[0]
+        nlam = len(gamma_n)
+        Wk = self.empty(nlam, d, m + p)
+        gn = (C.c_double * nlam)(*[float(g) for g in gamma_n])
+        info = (C.c_int * nlam)()
+        names = ("Gxx", "Gyx", "Gyy", "Gxu", "Gyu", "Guu", "GYy")
+        ptrs = [_ptr(_f64(G[k], k)) if G[k].numel() else C.c_void_p(0) for k in names]
+        rc = self.lib.nk_cv_weights(self.h, m, p, d, nlam, gn, float(jitter), *ptrs, _ptr(_f64(Kzz, "Kzz")), _ptr(Wk), info, self._stream())
+        if rc not in (0, -3):      # NK_E_NOT_SPD is reported per value through info (sklearn's error_score=nan semantics)
+            self._ck(rc, "nk_cv_weights")
+        return Wk, list(info)
+
+    def cv_score(self, Z, inv_ls, kind, Wk, X_aug, Y, p, sse=None):
+        """sse (nlam, d) += per-output squared error of Yhat = Wk [k(Z,x); u] over the held-out rows."""
+        nlam, d, _ = Wk.shape
+        m = Z.shape[0]
+        if sse is None:
+            sse = torch.zeros(nlam, d, dtype=torch.float64, device=self.tdev)
+        N = X_aug.shape[0]
+        self._ck(self.lib.nk_cv_score(self.h, _ptr(Z), Z.stride(0), m, d, int(p), _ptr(inv_ls), int(kind), _ptr(_f64(Wk, "Wk")), nlam * d,
+                                      _ptr(X_aug), X_aug.stride(0), _ptr(Y), Y.stride(0), N, _ptr(sse), self._stream()), "nk_cv_score")
+        return sse
 
     # ------------------------------------------------------------------ lift / predict / rollout
     def lift(self, Z, inv_ls, kind, Sinv, X_rows, transposed=False):

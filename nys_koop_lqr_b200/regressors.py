@@ -128,7 +128,7 @@ class KoopmanNystromRegressor(KoopmanRegressor):
 
     fit(X (n, d+p), Y (n, d)) -> None; lift(X (d, N)) -> (m, N); predict(X_aug (N, d+p)) -> (N, d).
     After fit: A (m,m), B (m,p), C (d,m), weights (d, m+p) are numpy float64; centres are (d, m) like upstream.
-    Additive API: ``forecast`` (batched open-loop rollout), ``fit_distributed`` (sample-sharded fit, one NCCL
+    Additive API: ``forecast`` (batched open-loop rollout), ``fit_cv`` (batched grid search), ``fit_distributed`` (sample-sharded fit, one NCCL
     allreduce of the Grams), ``stream_block`` (rows per host->device block of the streaming fit).
     """
 
@@ -285,6 +285,102 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         G = eng.gram_finalize()
         sharding.allreduce_grams(G["_flat"], group)                               # the only data-path collective
         self._solve(eng, dev, G, n_total, d)
+
+    def fit_cv(self, X, Y, kernels, gammas, n_splits=5, refit=True):
+        """Batched hyper-parameter search: the reference's ``learn_hyperparams`` (benchmark_lqr_cloth.py:39-66,
+        _classic.py:44-64, _hjb.py:47-71), i.e. ``GridSearchCV(estimator, {'kernel': kernels, 'gamma': gammas},
+        scoring='neg_root_mean_squared_error')`` with sklearn's default unshuffled ``KFold(n_splits)``, on the GPU.
+
+        Per kernel the samples stream through the fused lift+Gram kernel ONCE (one pass per fold block); a training
+        fold's Grams are the sum of the other folds' Grams; all gammas of a (kernel, fold) are factored as one batch
+        (``nk_cv_weights``) and scored together on the held-out block (``nk_cv_score``).  gamma_n = gamma * n_train
+        as in regressors.py:127.
+
+        Deviation from GridSearchCV, stated: every clone there redraws its landmarks from its own training fold with
+        the unseeded global RNG; here ONE landmark set (this estimator's centres, drawn from Y with the reference's
+        call if unset) is shared by all candidates and folds -- what sharing Grams across folds requires.
+        Returns a ``cv_results_``-style dict (same keys and candidate order as sklearn: gamma outer, kernel inner) and
+        sets ``cv_results_``, ``best_index_``, ``best_params_``, ``best_score_``; with ``refit`` the estimator is then
+        fitted on all samples with the best (kernel, gamma)."""
+        import torch
+        from scipy.stats import rankdata
+        kernels, gammas = list(kernels), [float(g) for g in gammas]
+        n = int(X.shape[0])
+        d = int(X.shape[1]) - self.n_inputs
+        p = self.n_inputs
+        if int(Y.shape[0]) != n or int(Y.shape[1]) != d:
+            raise ValueError("X must be (n, n_states + n_inputs) and Y (n, n_states)")
+        self._ensure_centers(lambda idx: self._rows_to_centers(Y, idx), n)
+        eng = _engine()
+        Xd, Yd = _as_device_rows(eng, X), _as_device_rows(eng, Y)
+        sizes = np.full(n_splits, n // n_splits, dtype=int)
+        sizes[: n % n_splits] += 1
+        stops = np.cumsum(sizes)
+        folds = [(int(e - s), int(e)) for s, e in zip(sizes, stops)]
+        Z = torch.from_numpy(np.ascontiguousarray(np.asarray(self.nystrom_centers_output, dtype=np.float64).T)).to(eng.tdev)
+        m = Z.shape[0]
+        scores = np.full((len(kernels), len(gammas), n_splits), np.nan)
+        prof = {"gram_s": 0.0, "weights_s": 0.0, "score_s": 0.0} if getattr(self, "cv_profile", False) else None
+
+        def tick():
+            if prof is None:
+                return 0.0
+            import time
+            torch.cuda.synchronize(eng.tdev)
+            return time.perf_counter()
+        for ki, holder in enumerate(kernels):
+            kind, ls = kernel_spec(holder, d)
+            inv_ls = torch.from_numpy(1.0 / ls).to(eng.tdev)
+            Kzz = eng.kzz(Z, inv_ls, kind)
+            fold_grams = []
+            t0 = tick()
+            for s, e in folds:                                   # one pass over the samples per kernel
+                eng.gram_begin(Z, inv_ls, kind, p, self.gram_chunk)
+                eng.gram_update(Xd[s:e], Yd[s:e])
+                fold_grams.append(eng.gram_finalize()["_flat"])
+            train = torch.empty_like(fold_grams[0])
+            if prof is not None:
+                prof["gram_s"] += tick() - t0
+            for fi, (s, e) in enumerate(folds):
+                t1 = tick()
+                train.zero_()
+                for fj in range(n_splits):
+                    if fj != fi:
+                        eng.axpy(1.0, fold_grams[fj], train)
+                n_train = n - (e - s)
+                Wk, info = eng.cv_weights(eng.gram_views(train, m, d, p), Kzz, [g * n_train for g in gammas], self.jitter)
+                t2 = tick()
+                sse = eng.cv_score(Z, inv_ls, kind, Wk, Xd[s:e], Yd[s:e], p).cpu().numpy()
+                if prof is not None:
+                    prof["weights_s"] += t2 - t1
+                    prof["score_s"] += tick() - t2
+                sc = -np.mean(np.sqrt(sse / (e - s)), axis=1)
+                sc[np.asarray(info) != 0] = np.nan               # sklearn error_score=nan for a candidate whose fit fails
+                scores[ki, :, fi] = sc
+            del fold_grams, train
+        # sklearn ParameterGrid order: keys sorted ('gamma' < 'kernel'), last key fastest
+        params, split = [], []
+        for gi, g in enumerate(gammas):
+            for ki, holder in enumerate(kernels):
+                params.append({"gamma": g, "kernel": holder})
+                split.append(scores[ki, gi])
+        split = np.array(split)
+        mean, std = split.mean(axis=1), split.std(axis=1)
+        res = {"params": params, "param_gamma": np.array([pp["gamma"] for pp in params]), "param_kernel": [pp["kernel"] for pp in params],
+               "mean_test_score": mean, "std_test_score": std,
+               "rank_test_score": rankdata(-np.where(np.isnan(mean), -np.inf, mean), method="min").astype(np.int32)}
+        for k in range(n_splits):
+            res[f"split{k}_test_score"] = split[:, k]
+        self.cv_results_ = res
+        self.cv_profile_ = prof
+        self.best_index_ = int(np.argmin(res["rank_test_score"]))
+        self.best_params_ = params[self.best_index_]
+        self.best_score_ = float(mean[self.best_index_])
+        if refit:
+            self.kernel = self.best_params_["kernel"]
+            self.gamma = self.best_params_["gamma"]
+            self.fit(Xd, Yd)
+        return res
 
     def lift(self, X):
         """regressors.py:171-178: X (d, N) column-samples -> phi = S^-1 k(Z, X), (m, N).  S^-1 is cached on the

@@ -206,6 +206,40 @@ def rmse_percent(true_traj, sim):
     return float(np.sqrt(np.sum(np.square(true_traj - sim))) / np.sqrt(np.sum(np.square(sim))) * 100)
 
 
+# --------------------------------------------------------------------------------------------
+# hyper-parameter search  (learn_hyperparams: benchmark_lqr_cloth.py:39-66, _classic.py:44-64, _hjb.py:47-71)
+# --------------------------------------------------------------------------------------------
+def kfold_bounds(n, n_splits=5):
+    """sklearn KFold(n_splits) without shuffling (GridSearchCV's default cv for a regressor): contiguous blocks, the
+    first n % n_splits of them one sample longer.  Returns [(start, stop), ...]."""
+    sizes = np.full(n_splits, n // n_splits, dtype=int)
+    sizes[: n % n_splits] += 1
+    stops = np.cumsum(sizes)
+    return [(int(e - s), int(e)) for s, e in zip(sizes, stops)]
+
+
+def neg_rmse(Y_true, Y_pred):
+    """sklearn 'neg_root_mean_squared_error' with multioutput='uniform_average': mean over outputs of per-output RMSE."""
+    return -float(np.mean(np.sqrt(np.mean(np.square(Y_true - Y_pred), axis=0))))
+
+
+def cv_scores(X_aug, Y, n_inputs, kinds_ls, gammas, Z, n_splits=5, solver="chol"):
+    """GridSearchCV restated with a fixed landmark set Z (m,d): for every kernel (kind, length_scale), gamma and fold,
+    fit on the training rows (gamma_n = gamma * n_train, regressors.py:127) and score `predict` on the held-out block.
+    Returns scores[kernel, gamma, fold]."""
+    X_aug = np.asarray(X_aug, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    n = X_aug.shape[0]
+    out = np.empty((len(kinds_ls), len(gammas), n_splits))
+    for ki, (kind, ls) in enumerate(kinds_ls):
+        for fi, (s, e) in enumerate(kfold_bounds(n, n_splits)):
+            tr = np.r_[0:s, e:n]
+            for gi, gamma in enumerate(gammas):
+                f = fit(X_aug[tr], Y[tr], n_inputs, kind, ls, gamma, Z=Z, solver=solver)
+                out[ki, gi, fi] = neg_rmse(Y[s:e], predict(f["W"], Z, X_aug[s:e], n_inputs, kind, ls, solver))
+    return out
+
+
 def dlqr(A, B, Q, R):
     """control.dlqr stand-in (benchmark_lqr_cloth.py:262): DARE + K = (B'PB+R)^-1 B'PA."""
     P = scipy.linalg.solve_discrete_are(A, B, Q, R)

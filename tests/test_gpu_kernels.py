@@ -216,3 +216,19 @@ def test_lift_predict_rollout(engine):
         true = Yt[:, b, :].T
         assert abs(np.sqrt(se / true.size) - O.rmse_cloth(true, sim)) <= 1e-12 * O.rmse_cloth(true, sim)
         assert abs(np.sqrt(se) / np.sqrt(ss) * 100 - O.rmse_percent(true, sim)) <= 1e-12 * O.rmse_percent(true, sim)
+
+
+def test_predict_more_rows_than_a_grid_dimension(engine):
+    """N > 65535 rows (regression: the control-column copy used the row count as grid.y)."""
+    rng = np.random.default_rng(0)
+    N, d, p, m = 70001, 2, 1, 20
+    Z = rng.standard_normal((m, d))
+    ls = np.array([1.0, 2.0])
+    Xa = rng.standard_normal((N, d + p))
+    W = rng.standard_normal((d, m + p))
+    Kmm = O.kernel_matrix(Z, Z, O.MATERN52, ls) + 1e-6 * np.eye(m)
+    w, V = np.linalg.eigh(Kmm)
+    Sinv = (V / np.sqrt(w)) @ V.T
+    got = host(engine.predict(dev(Z), dev(1.0 / ls), O.MATERN52, dev(Sinv), dev(W), dev(Xa), p))
+    want = (W @ np.vstack((Sinv @ O.kernel_matrix(Z, Xa[:, :d], O.MATERN52, ls), Xa[:, d:].T))).T
+    assert O.relerr(got, want) <= 1e-10
