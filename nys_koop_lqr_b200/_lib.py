@@ -8,7 +8,8 @@ import ctypes as C
 import pathlib
 
 _HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libnkb200.so"
+import os as _os
+LIB_PATH = pathlib.Path(_os.environ.get("NK_LIB_PATH", _HERE / "libnkb200.so"))   # override: development A/B builds only
 
 NK_KERNEL_RBF, NK_KERNEL_MATERN52 = 0, 1
 

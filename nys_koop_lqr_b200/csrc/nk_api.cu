@@ -225,6 +225,11 @@ int nk_gram_update(nk_handle *h, const double *X, long long ldx, const double *Y
     P.items = (const GramItem *)h->items.ptr;
     P.period_len = h->period_len; P.n_pk = h->n_pk; P.n_lf = h->n_lf; P.n_sy = h->n_sy;
     P.counters = (int *)h->counters.ptr;
+#ifdef NK_GRAM_TIMING
+    { int trc = ensure(h, h->dense[15], (size_t)h->sm_count * kConsumerWarps * 16 * sizeof(long long)); if (trc != NK_OK) return trc; }
+    P.timing = (long long *)h->dense[15].ptr;
+    NK_CUDA(h, cudaMemsetAsync(P.timing, 0, (size_t)h->sm_count * kConsumerWarps * 16 * sizeof(long long), stream));
+#endif
     NK_CUDA(h, cudaMemsetAsync(h->counters.ptr, 0, (size_t)(kCounterTileVer + h->ntiles) * sizeof(int), stream));
     cudaError_t e = cudaSuccess;
     launch_gram(P, h->sm_count, stream, &e);
@@ -234,6 +239,17 @@ int nk_gram_update(nk_handle *h, const double *X, long long ldx, const double *Y
     h->last_flops = (double)n_chunks * ((double)h->n_sy * per_tile * h->nk_chunk + (double)h->n_lf * per_tile * h->KLS * kSlabK);
     return NK_OK;
 }
+
+#ifdef NK_GRAM_TIMING
+// development build only: copies the per-warp cycle counters of the last nk_gram_update to the host (synchronises)
+int nk_debug_gram_timing(nk_handle *h, long long *out, int count) {
+    if (!h || !out || !h->dense[15].ptr) return NK_E_INVALID;
+    cudaDeviceSynchronize();
+    const size_t have = (size_t)h->sm_count * kConsumerWarps * 16;
+    cudaMemcpy(out, h->dense[15].ptr, sizeof(long long) * ((size_t)count < have ? (size_t)count : have), cudaMemcpyDeviceToHost);
+    return NK_OK;
+}
+#endif
 
 int nk_gram_finalize(nk_handle *h, double *Gxx, long long ld_gxx, double *Gyx, long long ld_gyx, double *Gyy, long long ld_gyy,
                      double *Gxu, long long ld_gxu, double *Gyu, long long ld_gyu, double *Guu, long long ld_guu,

@@ -481,17 +481,31 @@ void transpose_batched(nk_handle *h, int batch, int rows, int cols, const double
 int potrf_batched(nk_handle *h, int batch, int n, double *A, long long lda, long long sA, double *Lt, long long ldlt, long long sLt,
                   double *dinv, double *dinvT, long long sD, int *dinfo, cudaStream_t stream) {
     cudaMemsetAsync(dinfo, 0, sizeof(int) * batch, stream);
-    const int nblk = (n + kDB - 1) / kDB;
-    for (int kb = 0; kb < nblk; kb++) {
-        const int j0 = kb * kDB, nb = (n - j0 < kDB) ? n - j0 : kDB, rem = n - j0 - nb;
-        double *Akk = A + (long long)j0 * lda + j0;
-        double *di = dinv + (size_t)kb * kDB * kDB;
-        launch_diag(h, batch, Akk, lda, sA, nb, j0, di, dinvT ? dinvT + (size_t)kb * kDB * kDB : nullptr, sD, dinfo, 1, stream);
-        if (rem > 0) {
-            double *A21 = A + (long long)(j0 + nb) * lda + j0;
-            gemm_nt_batched(h, batch, rem, nb, nb, 1.0, A21, lda, sA, di, kDB, sD, 0.0, A21, lda, sA, 0.0, 0, nullptr, 0, 0, stream);
-            double *A22 = A + (long long)(j0 + nb) * lda + (j0 + nb);
-            gemm_nt_batched(h, batch, rem, rem, nb, -1.0, A21, lda, sA, A21, lda, sA, 1.0, A22, lda, sA, 0.0, kGemmLowerOnly, nullptr, 0, 0, stream);
+    // Two-level blocking.  Inside a 512-wide panel the 128-wide steps only update the panel's own remaining columns
+    // (short-K products, little work); everything to the right of the panel is updated ONCE per panel with K = 512,
+    // so the bulk of the n^3/3 flops runs in long-K GEMMs and the trailing matrix is read-modify-written n/512 times
+    // instead of n/128 times.
+    constexpr int kOuter = 4 * kDB;
+    for (int p0 = 0; p0 < n; p0 += kOuter) {
+        const int pend = (p0 + kOuter < n) ? p0 + kOuter : n;
+        for (int j0 = p0; j0 < pend; j0 += kDB) {
+            const int kb = j0 / kDB, nb = (pend - j0 < kDB) ? pend - j0 : kDB, j1 = j0 + nb, rem = n - j1, pc = pend - j1;
+            double *Akk = A + (long long)j0 * lda + j0;
+            double *di = dinv + (size_t)kb * kDB * kDB;
+            launch_diag(h, batch, Akk, lda, sA, nb, j0, di, dinvT ? dinvT + (size_t)kb * kDB * kDB : nullptr, sD, dinfo, 1, stream);
+            if (rem > 0) {
+                double *A21 = A + (long long)j1 * lda + j0;          // rows below the block, its nb columns
+                gemm_nt_batched(h, batch, rem, nb, nb, 1.0, A21, lda, sA, di, kDB, sD, 0.0, A21, lda, sA, 0.0, 0, nullptr, 0, 0, stream);
+                if (pc > 0)                                           // remaining columns of this panel (rectangular, K = nb)
+                    gemm_nt_batched(h, batch, rem, pc, nb, -1.0, A21, lda, sA, A21, lda, sA, 1.0, A + (long long)j1 * lda + j1, lda, sA, 0.0, 0,
+                                    nullptr, 0, 0, stream);
+            }
+        }
+        const int rem2 = n - pend;
+        if (rem2 > 0) {                                               // everything right of the panel, K = panel width
+            double *P = A + (long long)pend * lda + p0;
+            gemm_nt_batched(h, batch, rem2, rem2, pend - p0, -1.0, P, lda, sA, P, lda, sA, 1.0, A + (long long)pend * lda + pend, lda, sA, 0.0,
+                            kGemmLowerOnly, nullptr, 0, 0, stream);
         }
     }
     dim3 block(128), grid((n + 127) / 128, n, batch);

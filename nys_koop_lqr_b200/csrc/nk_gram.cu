@@ -8,8 +8,9 @@
 //
 //   pack(c)  : one 128-sample strip of chunk c -> scaled/centred/augmented sample operands for the lift GEMM
 //              ([x', -|x'|^2/2, 1] so that the accumulated value IS the exponent -r^2/2) and the raw [U;Y] rows.
-//   lift(c)  : 128 landmarks x 128 samples tile:  DMMA GEMM over d+2, kernel function in registers, tile
-//              stored straight from the C fragments into the packed feature chunk (L2-resident, evict_last).
+//   lift(c)  : 128 landmarks x 128 samples tile:  DMMA GEMM over d+2, kernel function applied on chip (exponents
+//              staged through shared memory, rolled loop), tile stored in C-fragment order straight into the packed
+//              feature chunk (L2-resident, evict_last).
 //   syrk(c)  : 128 x 128 output tile: DMMA contraction over the chunk's samples, accumulators added into the
 //              fragment-ordered accumulator workspace with cp.reduce.async.bulk ... add.f64 (UBLKRED).
 //
@@ -138,7 +139,7 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ double2 lds_v2(uint32_t addr) {
     double2 v;
-    asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ void sts_v2(uint32_t addr, double a, double b) {
@@ -287,11 +288,26 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                 pend_ver = nullptr;
             }
         };
+#ifdef NK_GRAM_TIMING
+        long long tm[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) tm[i] = 0;
+        const long long tm_begin = clock64();
+#define TM_START(v) long long v = clock64()
+#define TM_ADD(slot, v) tm[slot] += clock64() - (v)
+#define TM_COUNT(slot) tm[slot]++
+#else
+#define TM_START(v)
+#define TM_ADD(slot, v)
+#define TM_COUNT(slot)
+#endif
         for (;;) {
+            TM_START(t_iq);
             if (!mbar_try_wait(&ctl->iq_full[qslot], qphase)) {
                 flush_pending();      // never sit on a completion signal while idle: later items may be waiting for it
                 mbar_wait(&ctl->iq_full[qslot], qphase);
             }
+            TM_ADD(1, t_iq);
             const QueuedItem it = ctl->iq[qslot];
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->iq_empty[qslot]);
@@ -299,12 +315,14 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
             if (it.type < 0) { flush_pending(); break; }
 
             if (it.type == kItemPack) {
+                TM_START(t_pk);
                 flush_pending();
                 do_pack(P, it.chunk, it.a, tid);
                 fence_proxy_async();   // generic-proxy stores are read back through the async proxy (bulk copies)
                 __threadfence();
                 named_bar_sync(1, kConsumerWarps * 32);
                 if (tid == 0) atomicAdd(&P.counters[kCtrPack + (it.chunk & 1)], 1);
+                TM_ADD(2, t_pk);
                 continue;
             }
 
@@ -316,7 +334,10 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
 
             // ---- main loop: k8 steps with the first fragments of the NEXT step (and next slab) prefetched ----
             const int nslabs = (it.type == kItemLift) ? P.KLS : slabs_syrk;
+            TM_START(t_ff);
             mbar_wait_a(full0 + stage * 8, sphase);
+            TM_ADD(3, t_ff);
+            TM_START(t_ml);
             double2 b[4], nb[4], a0, na0;
             {
                 const uint32_t so = stage * (uint32_t)(2 * kSlabTileDoubles * 8);
@@ -341,7 +362,12 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                 a0 = na0;
                 // q = 1 (prefetch q = 0 of the next slab)
                 if (has_next) {
-                    if (!ready) mbar_wait_a(full0 + nstage * 8, nphase);
+                    if (!ready) {
+                        TM_START(t_mw);
+                        mbar_wait_a(full0 + nstage * 8, nphase);
+                        TM_ADD(11, t_mw);
+                        TM_COUNT(12);
+                    }
                     const uint32_t no = nstage * (uint32_t)(2 * kSlabTileDoubles * 8);
 #pragma unroll
                     for (int j = 0; j < 4; j++) nb[j] = lds_v2(b_off + no + j * 1024);
@@ -356,32 +382,47 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                 stage = nstage; sphase = nphase;
             }
 
+            TM_ADD((it.type == kItemLift) ? 4 : 5, t_ml);
+            TM_COUNT((it.type == kItemLift) ? 9 : 10);
+            TM_START(t_fl);
             flush_pending();
+            TM_ADD(6, t_fl);
+            TM_START(t_ep);
             if (it.type == kItemLift) {
-                // kernel function in registers, tile stored from the C fragments into the packed chunk
+                // The raw exponents go through this warp's staging buffer so that the kernel function runs in a ROLLED
+                // loop: applied straight to the 64 accumulator registers the code must be fully unrolled (static register
+                // indices), which with the double-precision exp / Matern bodies is ~240 KB of SASS that thrashes the
+                // instruction cache once per item (measured: the epilogue then costs as much as the item's main loop).
+                // Each lane reads back exactly what it wrote (no cross-lane traffic).
                 const int slot = it.chunk & 1;
                 double *psi = P.PSI[slot];
                 const long long s_chunk = (long long)it.chunk * P.nk;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int s_local = it.c * kTile + wc * 32 + j * 8;         // first sample of this 8-column block
-                    const long long s0 = s_chunk + s_local + 2 * t;
-                    const bool live0 = s0 < P.n, live1 = (s0 + 1) < P.n;
+                for (int i = 0; i < 8; i++)
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int lm = it.b * kTile + wr * 64 + i * 8 + g;          // landmark index
-                        const bool lm_ok = lm < P.m;
-                        const double v0 = (lm_ok && live0) ? kernel_from_exponent(acc[i][j][0], P.kind) : 0.0;
-                        const double v1 = (lm_ok && live1) ? kernel_from_exponent(acc[i][j][1], P.kind) : 0.0;
-                        const int R = it.a * P.MP + it.b * kTile + wr * 64 + i * 8;   // first row of the panel
-                        double *o = psi + packed_off(R, s_local, P.psi_rp) + lane * 2;
-                        st_v2_hint(o, v0, v1, pol_keep);
-                    }
+                    for (int j = 0; j < 4; j++) sts_v2(stg + (uint32_t)(i * 4 + j) * 512u + lane * 16u, acc[i][j][0], acc[i][j][1]);
+                __syncwarp();
+                const int kind = P.kind;
+                const int lm0 = it.b * kTile + wr * 64 + g;                       // landmark of fragment row block i = 0
+                const int sl0 = it.c * kTile + wc * 32;                           // first sample (chunk-local) of this warp tile
+                const int R0 = it.a * P.MP + it.b * kTile + wr * 64;              // first feature row of this warp tile
+#pragma unroll 1
+                for (int idx = 0; idx < 32; idx++) {
+                    const int i = idx >> 2, j = idx & 3;
+                    const double2 e = lds_v2(stg + (uint32_t)idx * 512u + lane * 16u);
+                    const int s_local = sl0 + j * 8;
+                    const long long s0 = s_chunk + s_local + 2 * t;
+                    const bool lm_ok = (lm0 + i * 8) < P.m;
+                    const double v0 = (lm_ok && s0 < P.n) ? kernel_from_exponent(e.x, kind) : 0.0;
+                    const double v1 = (lm_ok && (s0 + 1) < P.n) ? kernel_from_exponent(e.y, kind) : 0.0;
+                    double *o = psi + packed_off(R0 + i * 8, s_local, P.psi_rp) + lane * 2;
+                    st_v2_hint(o, v0, v1, pol_keep);
                 }
                 fence_proxy_async();
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) atomicAdd(&P.counters[kCtrLift + (it.chunk & 1)], 1);
+                TM_ADD(7, t_ep);
             } else {
                 // Gram epilogue: accumulators -> this warp's 16 KB staging buffer -> one asynchronous bulk reduce-add
                 // (TMA engine, SASS UBLKRED.ADD.F64) into the fragment-ordered accumulator tile.  The warp does not wait
@@ -403,8 +444,17 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                 }
                 pend_ver = ver;
                 pend_par = it.chunk & 1;
+                TM_ADD(8, t_ep);
             }
         }
+#ifdef NK_GRAM_TIMING
+        tm[0] = clock64() - tm_begin;
+        if (lane == 0 && P.timing != nullptr) {
+            long long *o = P.timing + ((size_t)blockIdx.x * kConsumerWarps + warp) * 16;
+#pragma unroll
+            for (int i = 0; i < 16; i++) o[i] = tm[i];
+        }
+#endif
     }
 }
 

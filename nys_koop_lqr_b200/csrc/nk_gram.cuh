@@ -31,6 +31,9 @@ struct GramParams {
     double *Gws;            // accumulator tiles in C-fragment order, 16384 doubles each
     const GramItem *items;  // one period: syrk(c) items with pack(c+1) and lift(c+1) items spliced in
     int period_len, n_pk, n_lf, n_sy;
+#ifdef NK_GRAM_TIMING
+    long long *timing;      // development build only: 16 cycle counters per consumer warp (tools/gram_timing.py)
+#endif
     int *counters;          // [0] next item; per chunk parity: [2+par] packs done, [4+par] lift warps done, [6+par] syrk warps done; [16+t] tile versions
 };
 
