@@ -479,7 +479,7 @@ void transpose_batched(nk_handle *h, int batch, int rows, int cols, const double
 // launches (grid.y / grid.x = batch), so the serial diagonal-block kernel of one matrix overlaps with the others'.
 // dinfo: `batch` device ints (0 or the 1-based index of the first non-positive pivot).
 int potrf_batched(nk_handle *h, int batch, int n, double *A, long long lda, long long sA, double *Lt, long long ldlt, long long sLt,
-                  double *dinv, double *dinvT, long long sD, int *dinfo, cudaStream_t stream) {
+                  double *dinv, double *dinvT, long long sD, int *dinfo, cudaStream_t stream, bool clean_upper) {
     cudaMemsetAsync(dinfo, 0, sizeof(int) * batch, stream);
     // Two-level blocking.  Inside a 512-wide panel the 128-wide steps only update the panel's own remaining columns
     // (short-K products, little work); everything to the right of the panel is updated ONCE per panel with K = 512,
@@ -508,16 +508,20 @@ int potrf_batched(nk_handle *h, int batch, int n, double *A, long long lda, long
                             kGemmLowerOnly, nullptr, 0, 0, stream);
         }
     }
-    dim3 block(128), grid((n + 127) / 128, n, batch);
-    zero_upper_kernel<<<grid, block, 0, stream>>>(n, A, lda, sA);
-    h->launches++;
+    // the strict upper triangle holds scratch values; the solves of this file never read it (they use the sub-diagonal
+    // blocks of L / the super-diagonal blocks of L^T and the inverted diagonal blocks), so it is only cleaned on request
+    if (clean_upper) {
+        dim3 block(128), grid((n + 127) / 128, n, batch);
+        zero_upper_kernel<<<grid, block, 0, stream>>>(n, A, lda, sA);
+        h->launches++;
+    }
     if (Lt) transpose_batched(h, batch, n, n, A, lda, sA, Lt, ldlt, sLt, stream);
     return NK_OK;
 }
 
 int potrf_blocked(nk_handle *h, int n, double *A, long long lda, double *Lt, long long ldlt, double *dinv, double *dinvT,
                   int *dinfo, cudaStream_t stream) {
-    return potrf_batched(h, 1, n, A, lda, 0, Lt, ldlt, 0, dinv, dinvT, 0, dinfo, stream);
+    return potrf_batched(h, 1, n, A, lda, 0, Lt, ldlt, 0, dinv, dinvT, 0, dinfo, stream, true);
 }
 
 // ---- triangular solves in transposed storage (Xt rows = right-hand sides) ----
@@ -543,21 +547,36 @@ void trsm_bwd_t(nk_handle *h, int n, int r, const double *Lt, long long ldlt, co
 // sL / sD / sX = 0 shares the factor / right-hand sides across the batch.
 void trsm_fwd_t_rl(nk_handle *h, int batch, int n, int r, const double *L, long long ldl, long long sL, const double *dinv, long long sD,
                    double *Xt, long long ldx, long long sX, cudaStream_t stream) {
-    const int nblk = (n + kDB - 1) / kDB;
-    for (int i = 0; i < nblk; i++) {
-        const int j0 = i * kDB, nb = (n - j0 < kDB) ? n - j0 : kDB, j1 = j0 + nb;
-        gemm_nt_batched(h, batch, r, nb, nb, 1.0, Xt + j0, ldx, sX, dinv + (size_t)i * kDB * kDB, kDB, sD, 0.0, Xt + j0, ldx, sX, 0.0, 0, nullptr, 0, 0, stream);
-        if (j1 < n) gemm_nt_batched(h, batch, r, n - j1, nb, -1.0, Xt + j0, ldx, sX, L + (long long)j1 * ldl + j0, ldl, sL, 1.0, Xt + j1, ldx, sX,
-                                    0.0, 0, nullptr, 0, 0, stream);
+    constexpr int kOuter = 4 * kDB;      // same two-level blocking as potrf_batched: the bulk of the update runs with K = 512
+    for (int p0 = 0; p0 < n; p0 += kOuter) {
+        const int pend = (p0 + kOuter < n) ? p0 + kOuter : n;
+        for (int j0 = p0; j0 < pend; j0 += kDB) {
+            const int nb = (pend - j0 < kDB) ? pend - j0 : kDB, j1 = j0 + nb, pc = pend - j1;
+            gemm_nt_batched(h, batch, r, nb, nb, 1.0, Xt + j0, ldx, sX, dinv + (size_t)(j0 / kDB) * kDB * kDB, kDB, sD, 0.0, Xt + j0, ldx, sX, 0.0, 0,
+                            nullptr, 0, 0, stream);
+            if (pc > 0) gemm_nt_batched(h, batch, r, pc, nb, -1.0, Xt + j0, ldx, sX, L + (long long)j1 * ldl + j0, ldl, sL, 1.0, Xt + j1, ldx, sX,
+                                        0.0, 0, nullptr, 0, 0, stream);
+        }
+        if (pend < n) gemm_nt_batched(h, batch, r, n - pend, pend - p0, -1.0, Xt + p0, ldx, sX, L + (long long)pend * ldl + p0, ldl, sL, 1.0,
+                                      Xt + pend, ldx, sX, 0.0, 0, nullptr, 0, 0, stream);
     }
 }
 void trsm_bwd_t_rl(nk_handle *h, int batch, int n, int r, const double *Lt, long long ldlt, long long sLt, const double *dinvT, long long sD,
                    double *Xt, long long ldx, long long sX, cudaStream_t stream) {
-    const int nblk = (n + kDB - 1) / kDB;
-    for (int i = nblk - 1; i >= 0; i--) {
-        const int j0 = i * kDB, nb = (n - j0 < kDB) ? n - j0 : kDB;
-        gemm_nt_batched(h, batch, r, nb, nb, 1.0, Xt + j0, ldx, sX, dinvT + (size_t)i * kDB * kDB, kDB, sD, 0.0, Xt + j0, ldx, sX, 0.0, 0, nullptr, 0, 0, stream);
-        if (j0 > 0) gemm_nt_batched(h, batch, r, j0, nb, -1.0, Xt + j0, ldx, sX, Lt + j0, ldlt, sLt, 1.0, Xt, ldx, sX, 0.0, 0, nullptr, 0, 0, stream);
+    constexpr int kOuter = 4 * kDB;
+    const int npan = (n + kOuter - 1) / kOuter;
+    for (int pi = npan - 1; pi >= 0; pi--) {
+        const int p0 = pi * kOuter, pend = (p0 + kOuter < n) ? p0 + kOuter : n;
+        const int nsub = (pend - p0 + kDB - 1) / kDB;
+        for (int si = nsub - 1; si >= 0; si--) {
+            const int j0 = p0 + si * kDB, nb = (pend - j0 < kDB) ? pend - j0 : kDB, pc = j0 - p0;
+            gemm_nt_batched(h, batch, r, nb, nb, 1.0, Xt + j0, ldx, sX, dinvT + (size_t)(j0 / kDB) * kDB * kDB, kDB, sD, 0.0, Xt + j0, ldx, sX, 0.0, 0,
+                            nullptr, 0, 0, stream);
+            if (pc > 0) gemm_nt_batched(h, batch, r, pc, nb, -1.0, Xt + j0, ldx, sX, Lt + (long long)p0 * ldlt + j0, ldlt, sLt, 1.0, Xt + p0, ldx, sX,
+                                        0.0, 0, nullptr, 0, 0, stream);
+        }
+        if (p0 > 0) gemm_nt_batched(h, batch, r, p0, pend - p0, -1.0, Xt + p0, ldx, sX, Lt + p0, ldlt, sLt, 1.0, Xt, ldx, sX, 0.0, 0, nullptr, 0, 0,
+                                    stream);
     }
 }
 

@@ -32,7 +32,7 @@ int potrf_blocked(nk_handle *h, int n, double *A, long long lda, double *Lt, lon
                   int *dinfo, cudaStream_t stream);
 // batched form: matrix b lives at A + b*sA (Lt + b*sLt, dinv + b*sD, ...); dinfo holds `batch` device ints
 int potrf_batched(nk_handle *h, int batch, int n, double *A, long long lda, long long sA, double *Lt, long long ldlt, long long sLt,
-                  double *dinv, double *dinvT, long long sD, int *dinfo, cudaStream_t stream);
+                  double *dinv, double *dinvT, long long sD, int *dinfo, cudaStream_t stream, bool clean_upper = false);
 // right-looking batched triangular solves for few right-hand sides (stride 0 = shared across the batch)
 void trsm_fwd_t_rl(nk_handle *h, int batch, int n, int r, const double *L, long long ldl, long long sL, const double *dinv, long long sD,
                    double *Xt, long long ldx, long long sX, cudaStream_t stream);
