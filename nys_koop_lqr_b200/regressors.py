@@ -358,7 +358,90 @@ class KoopmanNystromRegressor(KoopmanRegressor):
                 sc[np.asarray(info) != 0] = np.nan               # sklearn error_score=nan for a candidate whose fit fails
                 scores[ki, :, fi] = sc
             del fold_grams, train
-        # sklearn ParameterGrid order: keys sorted ('gamma' < 'kernel'), last key fastest
+        self.cv_profile_ = prof
+        return self._finish_cv(scores, kernels, gammas, n_splits, refit, lambda: self.fit(Xd, Yd))
+
+    def fit_cv_distributed(self, X_local, Y_local, kernels, gammas, n_splits=5, refit=True, group=None):
+        """`fit_cv` over several GPUs (one process per GPU, `torch.distributed`).  Every rank holds a contiguous block of the
+        samples; folds are sklearn's unshuffled KFold over the GLOBAL index.  Per kernel: each rank streams its part of
+        every fold through the fused kernel, ONE all_reduce sums the stacked per-fold Grams, the (fold, gamma-slice) solves
+        are dealt out round-robin (`sharding.cv_tasks`) and their prediction weights exchanged with one all_reduce of a
+        zero-filled buffer, every rank scores the held-out samples it owns, and one small all_reduce sums the squared
+        errors.  All ranks end with identical `cv_results_`; with `refit` the winner is fitted by `fit_distributed`."""
+        import torch
+        import torch.distributed as dist
+        from scipy.stats import rankdata
+        from . import sharding
+        kernels, gammas = list(kernels), [float(g) for g in gammas]
+        eng = _engine()
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        n_local = int(X_local.shape[0])
+        d = int(X_local.shape[1]) - self.n_inputs
+        p = self.n_inputs
+        n_total, off = sharding.global_layout(n_local, group, eng.tdev)
+        if self.nystrom_centers_output is None:
+            idx = np.random.choice(np.arange(0, n_total), size=self.m, replace=False)
+            rows_of = lambda loc: torch.from_numpy(np.ascontiguousarray(self._rows_to_centers(Y_local, loc).T))
+            Zc = sharding.assemble_landmarks(idx, off, n_local, rows_of, d, group, eng.tdev)
+            self.nystrom_centers_output = np.ascontiguousarray(Zc.cpu().numpy().T)
+        self._ensure_centers(None, n_total)
+        Xd, Yd = _as_device_rows(eng, X_local), _as_device_rows(eng, Y_local)
+        folds = sharding.kfold_bounds(n_total, n_splits)
+        local = sharding.fold_local_ranges(n_total, n_splits, off, n_local)
+        tasks = sharding.cv_tasks(n_splits, len(gammas), world)
+        Z = torch.from_numpy(np.ascontiguousarray(np.asarray(self.nystrom_centers_output, dtype=np.float64).T)).to(eng.tdev)
+        m, nlam = Z.shape[0], len(gammas)
+        scores = np.full((len(kernels), nlam, n_splits), np.nan)
+        for ki, holder in enumerate(kernels):
+            kind, ls = kernel_spec(holder, d)
+            inv_ls = torch.from_numpy(1.0 / ls).to(eng.tdev)
+            Kzz = eng.kzz(Z, inv_ls, kind)
+            stacked = None
+            for fi, (lo, hi) in enumerate(local):
+                eng.gram_begin(Z, inv_ls, kind, p, self.gram_chunk)
+                if hi > lo:
+                    eng.gram_update(Xd[lo:hi], Yd[lo:hi])
+                flat = eng.gram_finalize()["_flat"]
+                if stacked is None:
+                    stacked = torch.empty(n_splits, flat.numel(), dtype=torch.float64, device=eng.tdev)
+                stacked[fi].copy_(flat)
+            sharding.allreduce_sum(stacked, group)                                  # per-fold Grams of ALL samples
+            Wall = torch.zeros(n_splits, nlam, d, m + p, dtype=torch.float64, device=eng.tdev)
+            bad = torch.zeros(n_splits, nlam, dtype=torch.int32, device=eng.tdev)
+            train = torch.empty_like(stacked[0])
+            last_fold = -1
+            for trank, fi, g0, g1 in tasks:
+                if trank != rank:
+                    continue
+                if fi != last_fold:
+                    train.zero_()
+                    for fj in range(n_splits):
+                        if fj != fi:
+                            eng.axpy(1.0, stacked[fj], train)
+                    last_fold = fi
+                n_train = n_total - (folds[fi][1] - folds[fi][0])
+                Wk, info = eng.cv_weights(eng.gram_views(train, m, d, p), Kzz, [g * n_train for g in gammas[g0:g1]], self.jitter)
+                Wall[fi, g0:g1].copy_(Wk)
+                bad[fi, g0:g1] = torch.as_tensor(info, dtype=torch.int32, device=eng.tdev)
+            sharding.allreduce_sum(Wall, group)                                     # every slice was written by exactly one rank
+            sharding.allreduce_sum(bad, group)
+            sse = torch.zeros(n_splits, nlam, d, dtype=torch.float64, device=eng.tdev)
+            for fi, (lo, hi) in enumerate(local):
+                if hi > lo:
+                    eng.cv_score(Z, inv_ls, kind, Wall[fi], Xd[lo:hi], Yd[lo:hi], p, sse=sse[fi])
+            sharding.allreduce_sum(sse, group)
+            sse_h, bad_h = sse.cpu().numpy(), bad.cpu().numpy()
+            for fi, (s, e) in enumerate(folds):
+                sc = -np.mean(np.sqrt(sse_h[fi] / (e - s)), axis=1)
+                sc[bad_h[fi] != 0] = np.nan
+                scores[ki, :, fi] = sc
+            del stacked, Wall, train
+        return self._finish_cv(scores, kernels, gammas, n_splits, refit,
+                               lambda: self.fit_distributed(Xd, Yd, group=group))
+
+    def _finish_cv(self, scores, kernels, gammas, n_splits, refit, refit_fn):
+        """cv_results_ in sklearn's candidate order (ParameterGrid: keys sorted, 'gamma' outer, 'kernel' inner)."""
+        from scipy.stats import rankdata
         params, split = [], []
         for gi, g in enumerate(gammas):
             for ki, holder in enumerate(kernels):
@@ -372,14 +455,13 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         for k in range(n_splits):
             res[f"split{k}_test_score"] = split[:, k]
         self.cv_results_ = res
-        self.cv_profile_ = prof
         self.best_index_ = int(np.argmin(res["rank_test_score"]))
         self.best_params_ = params[self.best_index_]
         self.best_score_ = float(mean[self.best_index_])
         if refit:
             self.kernel = self.best_params_["kernel"]
             self.gamma = self.best_params_["gamma"]
-            self.fit(Xd, Yd)
+            refit_fn()
         return res
 
     def lift(self, X):

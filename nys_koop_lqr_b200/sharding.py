@@ -45,3 +45,46 @@ def allreduce_grams(flat, group=None):
     import torch.distributed as dist
     dist.all_reduce(flat, group=group)
     return flat
+
+
+# ---- cross-validation sweep over several GPUs ("CV sweep") ----------------------------------------------
+def kfold_bounds(n_total: int, n_splits: int):
+    """sklearn KFold(n_splits) without shuffling over the GLOBAL sample index: contiguous blocks, the first
+    n_total % n_splits one sample longer.  [(start, stop), ...]"""
+    sizes = np.full(n_splits, n_total // n_splits, dtype=np.int64)
+    sizes[: n_total % n_splits] += 1
+    stops = np.cumsum(sizes)
+    return [(int(e - s), int(e)) for s, e in zip(sizes, stops)]
+
+
+def fold_local_ranges(n_total: int, n_splits: int, offset: int, n_local: int):
+    """Intersection of every global fold with this rank's contiguous block, in LOCAL row indices.
+    [(lo, hi), ...] with lo == hi where the rank holds nothing of that fold."""
+    out = []
+    for s, e in kfold_bounds(n_total, n_splits):
+        lo, hi = max(s, offset), min(e, offset + n_local)
+        out.append((lo - offset, hi - offset) if hi > lo else (0, 0))
+    return out
+
+
+def cv_tasks(n_splits: int, n_gammas: int, world: int):
+    """The (fold, gamma-slice) solve tasks of one kernel and who runs them.  Every (fold, gamma) appears exactly once.
+    The gamma axis is cut into as many contiguous groups as it takes for the task count to be a multiple of the world size
+    (capped by the number of gammas): 5 folds on 8 ranks -> 8 groups -> 40 tasks, 5 per rank.
+    Returns [(rank, fold, g_lo, g_hi), ...]."""
+    from math import gcd
+    groups = max(1, min(n_gammas, world // gcd(world, n_splits)))
+    cuts = [round(i * n_gammas / groups) for i in range(groups + 1)]
+    tasks, t = [], 0
+    for f in range(n_splits):
+        for gi in range(groups):
+            if cuts[gi + 1] > cuts[gi]:
+                tasks.append((t % world, f, cuts[gi], cuts[gi + 1]))
+                t += 1
+    return tasks
+
+
+def allreduce_sum(t, group=None):
+    import torch.distributed as dist
+    dist.all_reduce(t, group=group)
+    return t

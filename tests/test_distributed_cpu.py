@@ -66,3 +66,68 @@ def test_sharded_grams_and_landmarks_world2():
         assert p_.exitcode == 0
     err = out.get(timeout=5)
     assert err <= 1e-13, f"shard-sum invariance violated: {err:.2e}"
+
+
+def test_cv_fold_ranges_and_tasks_cover_everything():
+    """Host logic of the multi-GPU CV sweep: global unshuffled folds cut by the rank blocks; every (fold, gamma) solved once."""
+    from nys_koop_lqr_b200 import sharding
+    from sklearn.model_selection import KFold
+    for n, k, w in ((1003, 5, 2), (2_000_000, 5, 8), (17, 3, 4), (100, 5, 1)):
+        want = [(int(te[0]), int(te[-1]) + 1) for _, te in KFold(k).split(np.zeros((n, 1)))] if n <= 5000 else sharding.kfold_bounds(n, k)
+        assert sharding.kfold_bounds(n, k) == want
+        covered = np.zeros((k, n), dtype=np.int8) if n <= 5000 else None
+        total = np.zeros(k, dtype=np.int64)
+        for r in range(w):
+            off, nl = sharding.shard_bounds(n, w, r)
+            for f, (lo, hi) in enumerate(sharding.fold_local_ranges(n, k, off, nl)):
+                assert 0 <= lo <= hi <= nl
+                total[f] += hi - lo
+                if covered is not None:
+                    covered[f, off + lo:off + hi] += 1
+        assert list(total) == [e - s for s, e in want]
+        if covered is not None:
+            for f, (s, e) in enumerate(want):
+                assert covered[f, s:e].min() == 1 and covered[f].sum() == e - s
+    for k, g, w in ((5, 16, 8), (5, 16, 1), (5, 3, 8), (3, 16, 2), (5, 1, 4)):
+        tasks = sharding.cv_tasks(k, g, w)
+        seen = np.zeros((k, g), dtype=int)
+        load = np.zeros(w)
+        for r, f, g0, g1 in tasks:
+            assert 0 <= r < w and g1 > g0
+            seen[f, g0:g1] += 1
+            load[r] += g1 - g0
+        assert (seen == 1).all()
+        if k * g >= w:
+            assert load.max() - load.min() <= max(1, np.ceil(g / max(1, w)))   # round-robin keeps the ranks balanced
+
+
+def _gather_worker(rank, world, port, out):
+    from nys_koop_lqr_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        k, g = 5, 6
+        W = torch.zeros(k, g, 3, 4, dtype=torch.float64)
+        for r, f, g0, g1 in sharding.cv_tasks(k, g, world):
+            if r == rank:
+                W[f, g0:g1] = torch.arange(f * 100 + g0, f * 100 + g1, dtype=torch.float64).view(-1, 1, 1)
+        sharding.allreduce_sum(W)                                  # exchange = sum of disjointly written slices
+        want = (torch.arange(k).view(-1, 1) * 100 + torch.arange(g).view(1, -1)).double().view(k, g, 1, 1).expand(k, g, 3, 4)
+        if rank == 0:
+            out.put(bool(torch.equal(W, want)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cv_weight_exchange_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    for p_ in procs:
+        p_.join(timeout=120)
+        assert p_.exitcode == 0
+    assert out.get(timeout=5)
