@@ -182,6 +182,8 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local_rank)
     distributed = world > 1
     if distributed:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # the image's default prints an "NCCL version" line on stdout next to the JSON line
         dist.init_process_group("nccl", device_id=dev)
     eng = Engine.get(local_rank)
     n, d, p, m = args.n, args.d, args.p, args.m
