@@ -15,6 +15,7 @@
 // Scoring multiplies the validation fold's kernel rows by the stacked weights of all nlam values at once.
 #include <vector>
 #include "nk_dense.cuh"
+#include "nk_pgemm.cuh"
 
 namespace nk {
 
@@ -81,7 +82,7 @@ __global__ void sse_columns_kernel(long long rows, int R, int d, const double *Y
 }
 
 int kernel_cross_t(nk_handle *h, const double *Z, long long ldz, int m, int d, const double *inv_ls, int kind,
-                   const double *X, long long ldx, long long N, double *Kt, long long ldkt, cudaStream_t stream);
+                   const double *X, long long ldx, long long N, double *Kt, long long ldkt, cudaStream_t stream, int packed_rp);
 void copy_cols(nk_handle *h, long long rows, int cols, const double *src, long long lds, double *dst, long long ldd, cudaStream_t stream);
 
 }  // namespace nk
@@ -190,20 +191,33 @@ int nk_cv_score(nk_handle *h, const double *Z, long long ldz, int m, int d, int 
     if (kind != NK_KERNEL_RBF && kind != NK_KERNEL_MATERN52) return set_err(h, NK_E_INVALID, "nk_cv_score: unsupported kernel kind");
     if (N == 0) return NK_OK;
     NK_CUDA(h, cudaSetDevice(h->device));
+    // Predictions of all stacked weight rows at once on the packed persistent GEMM (nk_pgemm.cu): the held-out block's kernel
+    // rows are written straight into the packed operand layout by the kernel-lift GEMM epilogue, the controls are dropped
+    // into the p spare contraction columns, the stacked weights are packed once per call.
     int rc;
-    const int N1 = m + p, ldf = even_c(N1);
-    long long nb = (1LL << 28) / (ldf + R);        // rows per block: <= 2 GiB of scratch for [K^T | U] and the predictions
-    nb = (nb / 128) * 128;
-    if (nb < 128) nb = 128;
-    if (nb > N) nb = N;
-    double *F = dense_scratch(h, 2, (size_t)nb * ldf, &rc); if (rc) return rc;
+    const int N1 = m + p, KS = (N1 + kSlabK - 1) / kSlabK, Kpad = KS * kSlabK;
+    const int RP = (int)pad_to(R, kTile);
+    long long nb = (1LL << 28) / (Kpad + R);        // rows per block: <= 2 GiB of scratch for [K^T | U] and the predictions
+    nb = (nb / kTile) * kTile;
+    if (nb < kTile) nb = kTile;
+    if (nb > pad_to(N, kTile)) nb = pad_to(N, kTile);
+    double *Fp = dense_scratch(h, 2, (size_t)nb * Kpad, &rc); if (rc) return rc;
     double *Yh = dense_scratch(h, 3, (size_t)nb * R, &rc); if (rc) return rc;
+    double *Wp = dense_scratch(h, 4, (size_t)RP * Kpad, &rc); if (rc) return rc;
+    NK_CUDA(h, cudaMemsetAsync(Fp, 0, (size_t)nb * Kpad * 8, stream));       // contraction padding must be exact zeros
+    NK_CUDA(h, cudaMemsetAsync(Wp, 0, (size_t)RP * Kpad * 8, stream));
+    pack_rows(h, Wk, N1, R, N1, Wp, RP / kPanel, 0, 0, stream);
+    const int rp_f = (int)(nb / kPanel);
     for (long long s = 0; s < N; s += nb) {
         const long long rows = (N - s < nb) ? N - s : nb;
         const double *Xb = X_aug + s * ldx;
-        if ((rc = kernel_cross_t(h, Z, ldz, m, d, inv_ls, kind, Xb, ldx, rows, F, ldf, stream)) != NK_OK) return rc;   // F[:, :m] = k(x, Z)
-        copy_cols(h, rows, p, Xb + d, ldx, F + m, ldf, stream);                                                       // F[:, m:] = u
-        gemm_nt(h, (int)rows, R, N1, 1.0, F, ldf, Wk, N1, 0.0, Yh, R, 0.0, 0, nullptr, 0, stream);
+        if ((rc = kernel_cross_t(h, Z, ldz, m, d, inv_ls, kind, Xb, ldx, rows, Fp, 0, stream, rp_f)) != NK_OK) return rc;   // k(x, Z), packed
+        if (p) pack_rows(h, Xb + d, ldx, rows, p, Fp, rp_f, 0, m, stream);                                               // u
+        PGemmParams P;
+        P.M = (int)rows; P.N = R; P.KS = KS; P.Ap = Fp; P.a_rp = rp_f; P.Bp = Wp; P.b_rp = RP / kPanel; P.alpha = 1.0; P.beta = 0.0;
+        P.C = Yh; P.ldc = R; P.c_col0 = 0; P.Cp = nullptr; P.c_rp = 0; P.cp_cols = 0;
+        P.tiles_m = (int)(pad_to(rows, kTile) / kTile); P.tiles_n = RP / kTile;
+        launch_pgemm(h, P, stream);
         sse_columns_kernel<<<(R + 31) / 32, dim3(32, 32), 0, stream>>>(rows, R, d, Yh, R, Y + s * ldy, ldy, sse);
         h->launches++;
     }

@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_kernel(GemmArgs g) {
                     if (g.beta != 0.0) v += g.beta * g.C[(long long)r * g.ldc + c];
                     if (r == c) v += g.diag;
                 }
+                if (g.flags & kGemmPackedOut) { g.C[packed_off(r, c, (int)g.ldc)] = v; continue; }
                 if (g.C) g.C[(long long)r * g.ldc + c] = v;
                 if (mirror && c != r) g.C[(long long)c * g.ldc + r] = v;
                 if (g.flags & kGemmStoreT) g.Ct[(long long)c * g.ldct + r] = v;

@@ -9,6 +9,7 @@ enum GemmFlags : int {
     kGemmStoreT = 2,      // store C^T (into Ct, ldct) in addition to C (C may be NULL)
     kGemmMirror = 4,      // with LowerOnly: also write the mirrored element so the full symmetric C is stored
     kGemmUnitDiag = 8,
+    kGemmPackedOut = 16,  // C is a PACKED operand buffer (nk_common.cuh layout, contraction index = result column); ldc = its row panels
 };
 
 // C (M,N) = alpha * A (M,K) * B(N,K)^T + beta * C  [+ diag * I],  all row-major ("NT": both operands k-contiguous)

@@ -6,6 +6,7 @@
 // Phi^T = K^T S^-1 (S^-1 symmetric), Yhat = [Phi^T | U] W^T, and a rollout step is Z_next = Z A^T (+ U_i B^T).
 // The recurrence stays serial in time exactly like the reference loop; only trajectories are batched.
 #include "nk_dense.cuh"
+#include "nk_pgemm.cuh"
 
 namespace nk {
 
@@ -43,8 +44,9 @@ void copy_cols(nk_handle *h, long long rows, int cols, const double *src, long l
 }
 
 // K^T = k(X, Z): (N, m), rows = points
+// packed_rp > 0: Kt is a packed operand buffer with that many 8-row panels (rows = points, contraction index = landmark)
 int kernel_cross_t(nk_handle *h, const double *Z, long long ldz, int m, int d, const double *inv_ls, int kind,
-                          const double *X, long long ldx, long long N, double *Kt, long long ldkt, cudaStream_t stream) {
+                   const double *X, long long ldx, long long N, double *Kt, long long ldkt, cudaStream_t stream, int packed_rp) {
     int rc;
     const int KA = even_i(d + 2);
     double *Za = dense_scratch(h, 0, (size_t)m * KA, &rc); if (rc) return rc;
@@ -53,7 +55,8 @@ int kernel_cross_t(nk_handle *h, const double *Z, long long ldz, int m, int d, c
     landmark_center(Z, ldz, m, d, ctr, stream);
     augment_rows(h, Z, ldz, m, d, inv_ls, ctr, 1, Za, KA, stream);
     augment_rows(h, X, ldx, N, d, inv_ls, ctr, 0, Xa, KA, stream);
-    gemm_nt(h, (int)N, m, KA, 1.0, Xa, KA, Za, KA, 0.0, Kt, ldkt, 0.0, 0, nullptr, 0, stream, kind);
+    if (packed_rp > 0) gemm_nt(h, (int)N, m, KA, 1.0, Xa, KA, Za, KA, 0.0, Kt, packed_rp, 0.0, kGemmPackedOut, nullptr, 0, stream, kind);
+    else gemm_nt(h, (int)N, m, KA, 1.0, Xa, KA, Za, KA, 0.0, Kt, ldkt, 0.0, 0, nullptr, 0, stream, kind);
     return NK_OK;
 }
 
@@ -75,7 +78,7 @@ int nk_lift(nk_handle *h, const double *Z, long long ldz, int m, int d, const do
     int rc;
     const int ldm = even_i(m);
     double *Kt = dense_scratch(h, 2, (size_t)N * ldm, &rc); if (rc) return rc;
-    if ((rc = kernel_cross_t(h, Z, ldz, m, d, inv_ls, kind, X, ldx, N, Kt, ldm, stream)) != NK_OK) return rc;
+    if ((rc = kernel_cross_t(h, Z, ldz, m, d, inv_ls, kind, X, ldx, N, Kt, ldm, stream, 0)) != NK_OK) return rc;
     // Phi^T (N,m) = K^T S^-1 ;  Phi (m,N) = S^-1 K  -- one product, stored both ways as requested
     const int flags = Phi ? kGemmStoreT : 0;
     gemm_nt(h, (int)N, m, m, 1.0, Kt, ldm, Sinv, ldsi, 0.0, PhiT, ldphit, 0.0, flags, Phi, ldphi, stream);
@@ -96,7 +99,7 @@ int nk_predict(nk_handle *h, const double *Z, long long ldz, int m, int d, int p
     const int ldm = even_i(m), ldf = even_i(m + p);
     double *Kt = dense_scratch(h, 2, (size_t)N * ldm, &rc); if (rc) return rc;
     double *F = dense_scratch(h, 3, (size_t)N * ldf, &rc); if (rc) return rc;    // [Phi^T | U] (N, m+p)
-    if ((rc = kernel_cross_t(h, Z, ldz, m, d, inv_ls, kind, X_aug, ldx, N, Kt, ldm, stream)) != NK_OK) return rc;
+    if ((rc = kernel_cross_t(h, Z, ldz, m, d, inv_ls, kind, X_aug, ldx, N, Kt, ldm, stream, 0)) != NK_OK) return rc;
     gemm_nt(h, (int)N, m, m, 1.0, Kt, ldm, Sinv, ldsi, 0.0, F, ldf, 0.0, 0, nullptr, 0, stream);
     copy_cols(h, N, p, X_aug + d, ldx, F + m, ldf, stream);
     gemm_nt(h, (int)N, d, m + p, 1.0, F, ldf, W, ldw, 0.0, Yhat, ldy, 0.0, 0, nullptr, 0, stream);
@@ -113,31 +116,61 @@ int nk_rollout(nk_handle *h, int m, int p, int d, int T, long long nb, const dou
         return set_err(h, NK_E_INVALID, "nk_rollout: bad argument");
     if (Ytrue && (!sq_err || !sq_sim)) return set_err(h, NK_E_INVALID, "nk_rollout: Ytrue needs sq_err and sq_sim");
     NK_CUDA(h, cudaSetDevice(h->device));
+    // One persistent packed-operand GEMM per time step (nk_pgemm.cu):
+    //     [ Z_{i+1} | Yhat_i ] = [ Z_i | U_i ] * [ A  B ; C  0 ]^T
+    // The lifted states stay in the packed operand layout from step to step (the epilogue writes Z_{i+1} with the result
+    // column as contraction index), the stacked model [A B; C 0] is packed once, and U_i is dropped into the p spare
+    // contraction columns of Z_i before each step.  The recurrence is serial in i exactly like the reference loop.
     int rc;
-    const int ldm = even_i(m);
-    double *Za = dense_scratch(h, 0, (size_t)nb * ldm, &rc); if (rc) return rc;
-    double *Zb = dense_scratch(h, 1, (size_t)nb * ldm, &rc); if (rc) return rc;
+    const int K = m + p, KS = (K + kSlabK - 1) / kSlabK;
+    const long long MPn = pad_to(nb, kTile);
+    const int rp_z = (int)(MPn / kPanel);
+    const int NWP = (int)pad_to(m + d, kTile), rp_w = NWP / kPanel;
+    const int NCP = (int)pad_to(d, kTile), rp_c = NCP / kPanel;
+    const size_t zdoubles = (size_t)KS * kSlabK * MPn;
+    double *Zp[2];
+    Zp[0] = dense_scratch(h, 0, zdoubles, &rc); if (rc) return rc;
+    Zp[1] = dense_scratch(h, 1, zdoubles, &rc); if (rc) return rc;
     double *Ystep = nullptr;
     if (!Yhat) { Ystep = dense_scratch(h, 2, (size_t)nb * d, &rc); if (rc) return rc; }
-    NK_CUDA(h, cudaMemcpy2DAsync(Za, (size_t)ldm * 8, Z0, (size_t)m * 8, (size_t)m * 8, nb, cudaMemcpyDeviceToDevice, stream));
+    double *Wp = dense_scratch(h, 3, (size_t)KS * kSlabK * NWP, &rc); if (rc) return rc;
+    double *Cpk = dense_scratch(h, 4, (size_t)KS * kSlabK * NCP, &rc); if (rc) return rc;
+    NK_CUDA(h, cudaMemsetAsync(Zp[0], 0, zdoubles * 8, stream));
+    NK_CUDA(h, cudaMemsetAsync(Zp[1], 0, zdoubles * 8, stream));
+    NK_CUDA(h, cudaMemsetAsync(Wp, 0, (size_t)KS * kSlabK * NWP * 8, stream));
+    NK_CUDA(h, cudaMemsetAsync(Cpk, 0, (size_t)KS * kSlabK * NCP * 8, stream));
+    pack_rows(h, A, m, m, m, Wp, rp_w, 0, 0, stream);
+    if (p) pack_rows(h, B, p, m, p, Wp, rp_w, 0, m, stream);
+    pack_rows(h, C, m, d, m, Wp, rp_w, m, 0, stream);
+    pack_rows(h, C, m, d, m, Cpk, rp_c, 0, 0, stream);
+    pack_rows(h, Z0, m, nb, m, Zp[0], rp_z, 0, 0, stream);
     if (Ytrue) {
         NK_CUDA(h, cudaMemsetAsync(sq_err, 0, (size_t)nb * 8, stream));
         NK_CUDA(h, cudaMemsetAsync(sq_sim, 0, (size_t)nb * 8, stream));
     }
     const int warps = 8;
+    int cur = 0;
     for (int i = 0; i < T; i++) {
         double *Yi = Yhat ? Yhat + (size_t)i * nb * d : Ystep;
-        gemm_nt(h, (int)nb, d, m, 1.0, Za, ldm, C, m, 0.0, Yi, d, 0.0, 0, nullptr, 0, stream);            // yhat_i = C z_i
+        PGemmParams P;
+        P.M = (int)nb; P.KS = KS; P.Ap = Zp[cur]; P.a_rp = rp_z; P.alpha = 1.0; P.beta = 0.0;
+        P.C = Yi; P.ldc = d; P.tiles_m = (int)(MPn / kTile);
+        if (i < T - 1) {
+            if (p) pack_rows(h, U + (size_t)i * nb * p, p, nb, p, Zp[cur], rp_z, 0, m, stream);
+            P.N = m + d; P.Bp = Wp; P.b_rp = rp_w; P.c_col0 = m;
+            P.Cp = Zp[cur ^ 1]; P.c_rp = rp_z; P.cp_cols = m; P.tiles_n = NWP / kTile;
+        } else {
+            P.N = d; P.Bp = Cpk; P.b_rp = rp_c; P.c_col0 = 0;          // last step: only yhat_{T-1} = C z_{T-1}
+            P.Cp = nullptr; P.c_rp = 0; P.cp_cols = 0; P.tiles_n = NCP / kTile;
+        }
+        launch_pgemm(h, P, stream);
         if (Ytrue) {
             step_error_kernel<<<(unsigned)((nb + warps - 1) / warps), warps * 32, 0, stream>>>(nb, d, Yi, Ytrue + (size_t)i * nb * d, sq_err, sq_sim);
             h->launches++;
         }
-        if (i == T - 1) break;
-        gemm_nt(h, (int)nb, m, m, 1.0, Za, ldm, A, m, 0.0, Zb, ldm, 0.0, 0, nullptr, 0, stream);           // z A^T
-        if (p) gemm_nt(h, (int)nb, m, p, 1.0, U + (size_t)i * nb * p, p, B, p, 1.0, Zb, ldm, 0.0, 0, nullptr, 0, stream);   // + u B^T
-        double *tmp = Za; Za = Zb; Zb = tmp;
+        if (i < T - 1) cur ^= 1;
     }
-    if (Zfinal) NK_CUDA(h, cudaMemcpy2DAsync(Zfinal, (size_t)m * 8, Za, (size_t)ldm * 8, (size_t)m * 8, nb, cudaMemcpyDeviceToDevice, stream));
+    if (Zfinal) unpack_rows(h, Zp[cur], rp_z, 0, 0, nb, m, Zfinal, m, stream);
     NK_CUDA(h, cudaGetLastError());
     return NK_OK;
 }

@@ -232,3 +232,29 @@ def test_predict_more_rows_than_a_grid_dimension(engine):
     got = host(engine.predict(dev(Z), dev(1.0 / ls), O.MATERN52, dev(Sinv), dev(W), dev(Xa), p))
     want = (W @ np.vstack((Sinv @ O.kernel_matrix(Z, Xa[:, :d], O.MATERN52, ls), Xa[:, d:].T))).T
     assert O.relerr(got, want) <= 1e-10
+
+
+@pytest.mark.parametrize("m,p,d,nb,T", [(57, 1, 2, 300, 7), (131, 0, 5, 129, 4), (260, 3, 192, 1, 12), (10, 2, 1, 1000, 1), (128, 6, 64, 257, 3)])
+def test_rollout_shapes(engine, m, p, d, nb, T):
+    """Packed persistent GEMM rollout on shapes that are not tile multiples (odd m, no controls, one trajectory, T = 1),
+    element-wise against the reference loop (benchmark_lqr_cloth.py:29-32) and the returned final lifted state."""
+    rng = np.random.default_rng(m + nb)
+    A = rng.standard_normal((m, m)) * (0.9 / np.sqrt(m))
+    B = rng.standard_normal((m, p))
+    Cm = rng.standard_normal((d, m))
+    z0 = rng.standard_normal((nb, m))
+    Uc = rng.standard_normal((max(T - 1, 0), nb, p))
+    Ud = dev(Uc) if (p and T > 1) else (torch.zeros(T - 1, nb, p, dtype=torch.float64).cuda() if T > 1 else None)
+    if T == 1:
+        res = engine.rollout(dev(A), dev(B) if p else None, dev(Cm), dev(z0), None, Ytrue=dev(rng.standard_normal((1, nb, d))), return_final=True)
+    else:
+        res = engine.rollout(dev(A), dev(B) if p else None, dev(Cm), dev(z0), Ud, return_final=True)
+    Yh = host(res["Yhat"])
+    assert Yh.shape == (T, nb, d)
+    for b in range(0, nb, max(1, nb // 7)):
+        sim = O.rollout(A, B, Cm, z0[b], Uc[:, b, :].T if T > 1 else np.zeros((p, 0)))
+        assert O.relerr(Yh[:, b, :].T, sim) <= 1e-12
+    z = z0.copy()
+    for i in range(T - 1):
+        z = z @ A.T + (Uc[i] @ B.T if p else 0.0)
+    assert O.relerr(host(res["Zfinal"]), z) <= 1e-12
