@@ -1,15 +1,21 @@
 #!/bin/bash
-# GPU call: full gpu test suite, then ncu evidence (launch list of the bench command + one full capture of the fused kernel)
+# GPU call: ncu evidence for the round (each capture only after the same command exited 0 without ncu)
 mkdir -p gpurun_out
-timeout -s KILL 900 python -m pytest tests -m gpu -q 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log
-# (1) launch list of the bench command (each launch once, gpu__time_duration only)
-timeout -s KILL 600 python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/bench_plain.json 2> gpurun_out/bench_plain.err &&
-timeout -s KILL 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/bench_ncu.json 2> gpurun_out/bench_ncu.err
+R=${ROUND:-r01b}
+# (1) launch list of the bench command
+timeout -s KILL 600 python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/${R}_bench_plain.json 2> gpurun_out/${R}_bench_plain.err &&
+timeout -s KILL 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${R}_launches.csv \
+    python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/${R}_bench_ncu.json 2> gpurun_out/${R}_bench_ncu.err
 echo "launch list rc=$?"
 # (2) full capture of the fused kernel on a short launch (65536 samples = 128 chunks)
-timeout -s KILL 300 python tools/perf_probe.py 65536 4096 192 6 512 0 > gpurun_out/probe_plain.log 2>&1 &&
-timeout -s KILL 1200 ncu --set full --clock-control none --import-source on -k regex:gram_kernel -c 1 -o gpurun_out/gram_full -f \
-    python tools/perf_probe.py 65536 4096 192 6 512 0 > gpurun_out/probe_ncu.log 2>&1
-echo "full capture rc=$?"
-ls -la gpurun_out | tail -20
+timeout -s KILL 300 python tools/perf_probe.py 65536 4096 192 6 512 0 > gpurun_out/${R}_probe_plain.log 2>&1 &&
+timeout -s KILL 1200 ncu --set full --clock-control none --import-source on -k regex:gram_kernel -c 1 -o gpurun_out/${R}_gram_full -f \
+    python tools/perf_probe.py 65536 4096 192 6 512 0 > gpurun_out/${R}_probe_ncu.log 2>&1
+echo "gram capture rc=$?"
+# (3) full capture of the packed persistent GEMM (one rollout step, 20000 trajectories, m=4096)
+timeout -s KILL 300 python tools/rollout_probe.py 20000 4096 3 > gpurun_out/${R}_rollout_plain.log 2>&1 &&
+timeout -s KILL 1200 ncu --set full --clock-control none --import-source on -k regex:pgemm_kernel -s 1 -c 1 -o gpurun_out/${R}_pgemm_full -f \
+    python tools/rollout_probe.py 20000 4096 3 > gpurun_out/${R}_rollout_ncu.log 2>&1
+echo "pgemm capture rc=$?"
+cat gpurun_out/${R}_rollout_plain.log | tail -2
+ls -la gpurun_out | tail -12
