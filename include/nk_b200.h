@@ -106,6 +106,13 @@ int nk_rollout(nk_handle *h, int m, int p, int d, int T, long long nb, const dou
                const double *Z0, const double *U, double *Yhat, const double *Ytrue, double *sq_err, double *sq_sim,
                double *Zfinal, void *stream);
 
+/* ---- batched closed loop in the lifted space (benchmark_lqr_cloth.py:69-104 `lqr_control`, lines 80-84 for one trajectory) ----
+ *     u_i = K (phi_ref - z_i);   x_i = C z_i;   z_{i+1} = A z_i + B u_i,    i = 0..steps-1   (serial in i, same operation order)
+ *   Z0 (nb, m) lifted initial states, Zref (nb, m) lifted references, K (p, m) gain (control.dlqr, computed on the host).
+ *   Xs (steps, nb, d) visited states, Us (steps, nb, p) control increments, Zfinal (nb, m) optional. */
+int nk_closed_loop(nk_handle *h, int m, int p, int d, int steps, long long nb, const double *A, const double *B, const double *C,
+                   const double *K, const double *Z0, const double *Zref, double *Xs, double *Us, double *Zfinal, void *stream);
+
 /* ---- cross-validation sweep over the (kernel, gamma) grid: learn_hyperparams in benchmark_lqr_hjb.py:47-71,
  * benchmark_lqr_classic.py:44-64, benchmark_lqr_cloth.py:39-66 (sklearn GridSearchCV cloning the estimator per candidate and
  * fold, `fit` on the training fold, score = RMSE of `predict` (regressors.py:48-55) on the held-out fold) ----

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "nk_lift": ([C.c_void_p, _c_dp, _ll, _i, _i, _c_dp, _i, _c_dp, _ll, _c_dp, _ll, _ll, _c_dp, _ll, _c_dp, _ll, C.c_void_p], _i),
     "nk_predict": ([C.c_void_p, _c_dp, _ll, _i, _i, _i, _c_dp, _i, _c_dp, _ll, _c_dp, _ll, _c_dp, _ll, _ll, _c_dp, _ll, C.c_void_p], _i),
     "nk_rollout": ([C.c_void_p, _i, _i, _i, _i, _ll] + [_c_dp] * 10 + [C.c_void_p], _i),
+    "nk_closed_loop": ([C.c_void_p, _i, _i, _i, _i, _ll] + [_c_dp] * 9 + [C.c_void_p], _i),
     "nk_cv_weights": ([C.c_void_p, _i, _i, _i, _i, C.POINTER(_d), _d] + [_c_dp] * 9 + [C.POINTER(_i), C.c_void_p], _i),
     "nk_cv_score": ([C.c_void_p, _c_dp, _ll, _i, _i, _i, _c_dp, _i, _c_dp, _i, _c_dp, _ll, _c_dp, _ll, _ll, _c_dp, C.c_void_p], _i),
     "nk_axpy": ([C.c_void_p, _ll, _d, _c_dp, _c_dp, C.c_void_p], _i),

@@ -43,6 +43,11 @@ void copy_cols(nk_handle *h, long long rows, int cols, const double *src, long l
     h->launches++;
 }
 
+// out = a - b over a whole packed buffer (both operands share the layout, so the difference of two packed matrices is elementwise)
+__global__ void sub_kernel(long long n, const double *a, const double *b, double *out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = a[i] - b[i];
+}
+
 // K^T = k(X, Z): (N, m), rows = points
 // packed_rp > 0: Kt is a packed operand buffer with that many 8-row panels (rows = points, contraction index = landmark)
 int kernel_cross_t(nk_handle *h, const double *Z, long long ldz, int m, int d, const double *inv_ls, int kind,
@@ -169,6 +174,63 @@ int nk_rollout(nk_handle *h, int m, int p, int d, int T, long long nb, const dou
             h->launches++;
         }
         if (i < T - 1) cur ^= 1;
+    }
+    if (Zfinal) unpack_rows(h, Zp[cur], rp_z, 0, 0, nb, m, Zfinal, m, stream);
+    NK_CUDA(h, cudaGetLastError());
+    return NK_OK;
+}
+
+int nk_closed_loop(nk_handle *h, int m, int p, int d, int steps, long long nb, const double *A, const double *B, const double *C,
+                   const double *K, const double *Z0, const double *Zref, double *Xs, double *Us, double *Zfinal, void *stream_) {
+    if (!h) return NK_E_INVALID;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (m < 1 || p < 1 || d < 1 || steps < 1 || nb < 1 || nb > 2000000000LL || !A || !B || !C || !K || !Z0 || !Zref || !Xs || !Us)
+        return set_err(h, NK_E_INVALID, "nk_closed_loop: bad argument");
+    NK_CUDA(h, cudaSetDevice(h->device));
+    // Per step, in the reference's order of operations (benchmark_lqr_cloth.py:80-84):
+    //   u_i = K (phi_ref - z_i)          packed difference (elementwise), then a p-column packed GEMM
+    //   [ z_{i+1} | x_i ] = [ z_i | u_i ] [ A B ; C 0 ]^T     the rollout step of nk_rollout
+    int rc;
+    const int Kc = m + p, KS = (Kc + kSlabK - 1) / kSlabK;
+    const long long MPn = pad_to(nb, kTile);
+    const int rp_z = (int)(MPn / kPanel);
+    const int NWP = (int)pad_to(m + d, kTile), rp_w = NWP / kPanel;
+    const int NKP = (int)pad_to(p, kTile), rp_k = NKP / kPanel;
+    const size_t zdoubles = (size_t)KS * kSlabK * MPn;
+    double *Zp[2];
+    Zp[0] = dense_scratch(h, 0, zdoubles, &rc); if (rc) return rc;
+    Zp[1] = dense_scratch(h, 1, zdoubles, &rc); if (rc) return rc;
+    double *Rp = dense_scratch(h, 2, zdoubles, &rc); if (rc) return rc;      // packed phi_ref
+    double *Wp = dense_scratch(h, 3, (size_t)KS * kSlabK * NWP, &rc); if (rc) return rc;
+    double *Kp = dense_scratch(h, 4, (size_t)KS * kSlabK * NKP, &rc); if (rc) return rc;
+    double *Dp = dense_scratch(h, 5, zdoubles, &rc); if (rc) return rc;      // packed phi_ref - z_i
+    NK_CUDA(h, cudaMemsetAsync(Zp[0], 0, zdoubles * 8, stream));
+    NK_CUDA(h, cudaMemsetAsync(Zp[1], 0, zdoubles * 8, stream));
+    NK_CUDA(h, cudaMemsetAsync(Rp, 0, zdoubles * 8, stream));
+    NK_CUDA(h, cudaMemsetAsync(Wp, 0, (size_t)KS * kSlabK * NWP * 8, stream));
+    NK_CUDA(h, cudaMemsetAsync(Kp, 0, (size_t)KS * kSlabK * NKP * 8, stream));
+    pack_rows(h, A, m, m, m, Wp, rp_w, 0, 0, stream);
+    pack_rows(h, B, p, m, p, Wp, rp_w, 0, m, stream);
+    pack_rows(h, C, m, d, m, Wp, rp_w, m, 0, stream);
+    pack_rows(h, K, m, p, m, Kp, rp_k, 0, 0, stream);
+    pack_rows(h, Z0, m, nb, m, Zp[0], rp_z, 0, 0, stream);
+    pack_rows(h, Zref, m, nb, m, Rp, rp_z, 0, 0, stream);
+    const long long sub_blocks = ((long long)zdoubles + 255) / 256;
+    int cur = 0;
+    for (int i = 0; i < steps; i++) {
+        double *Ui = Us + (size_t)i * nb * p, *Xi = Xs + (size_t)i * nb * d;
+        sub_kernel<<<(unsigned)(sub_blocks < 16384 ? sub_blocks : 16384), 256, 0, stream>>>((long long)zdoubles, Rp, Zp[cur], Dp);
+        h->launches++;
+        PGemmParams P;
+        P.M = (int)nb; P.KS = KS; P.alpha = 1.0; P.beta = 0.0; P.tiles_m = (int)(MPn / kTile);
+        P.Ap = Dp; P.a_rp = rp_z; P.Bp = Kp; P.b_rp = rp_k; P.N = p; P.C = Ui; P.ldc = p; P.c_col0 = 0;
+        P.Cp = nullptr; P.c_rp = 0; P.cp_cols = 0; P.tiles_n = NKP / kTile;
+        launch_pgemm(h, P, stream);                                            // u_i = (phi_ref - z_i) K^T
+        pack_rows(h, Ui, p, nb, p, Zp[cur], rp_z, 0, m, stream);
+        P.Ap = Zp[cur]; P.Bp = Wp; P.b_rp = rp_w; P.N = m + d; P.C = Xi; P.ldc = d; P.c_col0 = m;
+        P.Cp = Zp[cur ^ 1]; P.c_rp = rp_z; P.cp_cols = m; P.tiles_n = NWP / kTile;
+        launch_pgemm(h, P, stream);                                            // x_i = C z_i, z_{i+1} = A z_i + B u_i
+        cur ^= 1;
     }
     if (Zfinal) unpack_rows(h, Zp[cur], rp_z, 0, 0, nb, m, Zfinal, m, stream);
     NK_CUDA(h, cudaGetLastError());

@@ -209,6 +209,17 @@ class Engine:
                                        _ptr(Cm), _ptr(W), C.byref(info), self._stream()), "nk_solve_abc")
         return A, B, Cm, W
 
+    def closed_loop(self, A, B, Cm, K, Z0, Zref, steps, return_final=False):
+        """Batched lifted closed loop. Z0, Zref (nb, m); K (p, m). Returns Xs (steps, nb, d), Us (steps, nb, p)[, Zfinal]."""
+        nb, m = Z0.shape
+        d, p = Cm.shape[0], K.shape[0]
+        Xs, Us = self.empty(steps, nb, d), self.empty(steps, nb, p)
+        Zf = self.empty(nb, m) if return_final else None
+        self._ck(self.lib.nk_closed_loop(self.h, m, p, d, int(steps), nb, _ptr(_f64(A, "A")), _ptr(_f64(B, "B")), _ptr(_f64(Cm, "C")),
+                                         _ptr(_f64(K, "K")), _ptr(_f64(Z0, "Z0")), _ptr(_f64(Zref, "Zref")), _ptr(Xs), _ptr(Us), _ptr(Zf),
+                                         self._stream()), "nk_closed_loop")
+        return (Xs, Us, Zf) if return_final else (Xs, Us)
+
     # ------------------------------------------------------------------ cross-validation sweep
     def axpy(self, alpha, x, y):
         """y += alpha * x on the device (flat float64 buffers of equal length)."""

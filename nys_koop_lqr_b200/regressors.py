@@ -539,6 +539,36 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         return sim, rmse, pct
 
 
+# (closed_loop is attached to KoopmanNystromRegressor below)
+def _closed_loop(self, K, initial_states, references, num_steps):
+    """Batched lifted closed loop: `lqr_control` of benchmark_lqr_cloth.py:69-104 (loop body :80-84) for many
+    (initial state, reference) pairs at once.  K (p, m) is the LQR gain (``control.dlqr`` on the host, as upstream);
+    initial_states, references: (d, nb) (or (d,) / (d,1) for one).  Returns (states (d, num_steps, nb), controls
+    (p, num_steps, nb)): states[:, i] = C z_i, controls[:, i] = K (phi_ref - z_i), z_{i+1} = A z_i + B u_i."""
+    import torch
+    x0 = np.asarray(initial_states, dtype=np.float64)
+    xr = np.asarray(references, dtype=np.float64)
+    single = x0.ndim == 1 or x0.shape[1] == 1
+    x0, xr = x0.reshape(x0.shape[0], -1), xr.reshape(xr.shape[0], -1)
+    d = x0.shape[0]
+    dev = self._device_state(d)
+    eng = dev["eng"]
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64))).to(eng.tdev)
+    Z0 = eng.lift(dev["Z"], dev["inv_ls"], dev["kind"], dev["Sinv"], to(x0.T), transposed=True)
+    Zr = eng.lift(dev["Z"], dev["inv_ls"], dev["kind"], dev["Sinv"], to(xr.T), transposed=True)
+    if Zr.shape[0] == 1 and Z0.shape[0] > 1:
+        Zr = Zr.expand(Z0.shape[0], -1).contiguous()
+    Xs, Us = eng.closed_loop(to(self.A), to(self.B), to(self.C), to(K), Z0, Zr, int(num_steps))
+    states = np.transpose(Xs.cpu().numpy(), (2, 0, 1))
+    controls = np.transpose(Us.cpu().numpy(), (2, 0, 1))
+    if single:
+        return states[:, :, 0], controls[:, :, 0]
+    return states, controls
+
+
+KoopmanNystromRegressor.closed_loop = _closed_loop
+
+
 # ----------------------------------------------------------------------------------------------
 # out-of-scope baselines (regressors.py:58-111 exact-kernel, :181-234 thin-plate splines): not part of the B200
 # hot path (SURVEY 2.1).  They are re-exported from an upstream checkout when one is reachable so that the

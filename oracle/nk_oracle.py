@@ -196,6 +196,20 @@ def rollout(A, B, C, z0, controls):
     return out
 
 
+def closed_loop(A, B, C, K, z0, zref, num_steps):
+    """benchmark_lqr_cloth.py:80-84 (lqr_control loop body) for one trajectory: u = K (phi_ref - phi); state = C phi;
+    phi <- A phi + B u.  z0, zref (m,).  Returns states (d, num_steps), controls (p, num_steps)."""
+    z = np.asarray(z0, dtype=np.float64).reshape(-1, 1)
+    zr = np.asarray(zref, dtype=np.float64).reshape(-1, 1)
+    xs, us = [], []
+    for _ in range(num_steps):
+        u = K @ (zr - z)
+        us.append(u[:, 0])
+        xs.append((C @ z)[:, 0])
+        z = A @ z + B @ u
+    return np.array(xs).T, np.array(us).T
+
+
 def rmse_cloth(true_traj, sim):
     """benchmark_lqr_cloth.py:34"""
     return float(np.sqrt(np.mean(np.square(true_traj - sim))))

@@ -258,3 +258,20 @@ def test_rollout_shapes(engine, m, p, d, nb, T):
     for i in range(T - 1):
         z = z @ A.T + (Uc[i] @ B.T if p else 0.0)
     assert O.relerr(host(res["Zfinal"]), z) <= 1e-12
+
+
+@pytest.mark.parametrize("m,p,d,nb,steps", [(80, 2, 12, 5, 30), (131, 6, 192, 130, 6), (20, 1, 2, 1, 60)])
+def test_closed_loop_against_reference_loop(engine, m, p, d, nb, steps):
+    """Batched lifted closed loop vs the reference's lqr_control loop body (benchmark_lqr_cloth.py:80-84), same operation order."""
+    rng = np.random.default_rng(m * 7 + nb)
+    A = rng.standard_normal((m, m)) * (0.6 / np.sqrt(m))
+    B = rng.standard_normal((m, p)) * 0.3
+    Cm = rng.standard_normal((d, m))
+    K, _ = O.dlqr(A, B, np.eye(m), np.eye(p))        # any stabilising gain; DARE stays on the host
+    z0, zr = rng.standard_normal((nb, m)), rng.standard_normal((nb, m))
+    Xs, Us, Zf = engine.closed_loop(dev(A), dev(B), dev(Cm), dev(K), dev(z0), dev(zr), steps, return_final=True)
+    Xs, Us = host(Xs), host(Us)
+    for b in range(0, nb, max(1, nb // 5)):
+        xs, us = O.closed_loop(A, B, Cm, K, z0[b], zr[b], steps)
+        assert O.relerr(Xs[:, b, :].T, xs) <= 1e-11
+        assert O.relerr(Us[:, b, :].T, us) <= 1e-11
