@@ -9,7 +9,7 @@ The scripts are not modified: each is loaded as a module (its `__main__` block d
 (`n_inputs`, `n_states`, `dynamical_system`) are set the way its `__main__` sets them.  The reference tree is read
 from NK_REFERENCE_PATH (default: /root/reference, else baseline/_ref staged by tools/stage_reference.sh -- git-ignored).
 
-    python tools/run_reference_scripts.py [--quick] [--out profiles/r01_reference_scripts_parity.md]
+    python tests/harness/run_reference_scripts.py [--quick] [--out profiles/r01_reference_scripts_parity.md]
 """
 from __future__ import annotations
 
@@ -25,7 +25,7 @@ import types
 import numpy as np
 import scipy.linalg
 
-ROOT = pathlib.Path(__file__).resolve().parents[1]
+ROOT = pathlib.Path(__file__).resolve().parents[2]
 
 
 def find_reference() -> pathlib.Path:
@@ -361,7 +361,7 @@ def main():
     out.parent.mkdir(parents=True, exist_ok=True)
     with open(out, "w") as f:
         f.write("# Reference scripts: B200 drop-in vs unmodified reference (same seeds)\n\n")
-        f.write("Produced by `tools/run_reference_scripts.py` on the GPU box: the scripts' own functions (`validate_dyn_sys`, `lqr_control`, "
+        f.write("Produced by `tests/harness/run_reference_scripts.py` on the GPU box: the scripts' own functions (`validate_dyn_sys`, `lqr_control`, "
                 "`create_data_matrices`, `generate_dataset`, `simulate_true_system`) run unmodified against both `regressors` modules. "
                 "`err` = relative error of the B200 result w.r.t. the reference; `self-floor` = how far the reference moves from itself "
                 "when its training samples are permuted (same landmarks) -- where cond(inner_term) is large that is the meaningful yardstick (SURVEY 8c).\n\n")

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Stages the files tools/run_reference_scripts.py needs from the read-only reference mount into baseline/_ref/
+# Stages the files tests/harness/run_reference_scripts.py needs from the read-only reference mount into baseline/_ref/
 # (git-ignored, NOT gpurun-ignored: it travels to the GPU box, it never enters the history).
 set -e
 SRC=${1:-/root/reference}
