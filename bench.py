@@ -137,7 +137,8 @@ def workload_config(args, n_gpus):
         "workload": f"synthetic Koopman fit n={args.n} samples, d={args.d}, p={args.p}, m={args.m} landmarks, FP64 (BASELINE.json configs[3])",
         "n": args.n, "d": args.d, "p": args.p, "m": args.m, "kernel": "RBF length_scale=10 (ThreeDimensionalKernel(10,10,10,d))", "gamma": args.gamma,
         "generator": "x~N(0,I), u~N(0,I), y=tanh(x M^T)+u Bu^T (SURVEY 8d), generated on device per shard",
-        "parallelism": f"sample-sharded x{n_gpus}, one allreduce of the Grams" if n_gpus > 1 else "single GPU",
+        "parallelism": (f"sample-sharded x{n_gpus} (rank 0's block shorter by the landmark-only stage it owns), one allreduce of the Grams, "
+                        f"one broadcast of S, S^-1") if n_gpus > 1 else "single GPU",
         "l2": "inputs (31.2 GB) are far larger than L2; no flush needed between steps",
     }
 
@@ -187,14 +188,17 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     eng = Engine.get(local_rank)
     n, d, p, m = args.n, args.d, args.p, args.m
-    n_local = n // world + (1 if rank < n % world else 0)
+    from nys_koop_lqr_b200 import sharding
+    # rank 0 also owns the landmark-only stage of the fit (square root of K_mm): its block is shorter by that much work
+    head = sharding.head_samples(m, d, p) if world > 1 else 0
+    counts = [sharding.balanced_bounds(n, world, r, head)[1] for r in range(world)]
+    n_local = counts[rank]
 
     # ---- data (untimed) ----
     X, Y, Xh, Yh = generate_shard(torch, dev, n_local, d, p, seed=1000 + rank, pinned=not args.no_e2e)
     # landmarks: the reference's draw over the GLOBAL index (regressors.py:129-132), same RNG state on every rank
     np.random.seed(0)
     idx = np.random.choice(np.arange(0, n), size=m, replace=False)
-    counts = [n // world + (1 if r < n % world else 0) for r in range(world)]
     off = int(np.sum(counts[:rank]))
     Zbuf = torch.zeros(m, d, dtype=torch.float64, device=dev)
     mine = np.nonzero((idx >= off) & (idx < off + n_local))[0]

@@ -148,24 +148,34 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         state.pop("_dev", None)
         return state
 
-    def _device_state(self, n_states):
-        """Landmarks, 1/l, K_zz, S, S^-1 on the device; rebuilt lazily (e.g. after unpickling)."""
+    def _device_state(self, n_states, landmark_stage=True):
+        """Landmarks, 1/l, K_zz, S, S^-1 on the device; rebuilt lazily (e.g. after unpickling).  With
+        ``landmark_stage=False`` only the landmarks and 1/l are set up (K_zz, S, S^-1 are filled in later: the
+        sample-sharded fit computes them on one rank and broadcasts them)."""
         import torch
         dev = self.__dict__.get("_dev")
         Zc = self.nystrom_centers_output
-        if dev is not None and dev["src"] is Zc and dev["kernel"] is self.kernel:
+        if dev is not None and dev["src"] is Zc and dev["kernel"] is self.kernel and (dev.get("S") is not None or not landmark_stage):
             return dev
         eng = _engine()
         kind, ls = kernel_spec(self.kernel, n_states)
         Z = torch.from_numpy(np.ascontiguousarray(np.asarray(Zc, dtype=np.float64).T)).to(eng.tdev)   # (m, d) rows
         inv_ls = torch.from_numpy(1.0 / ls).to(eng.tdev)
-        Kzz = eng.kzz(Z, inv_ls, kind)
-        Kmm = Kzz.clone()
-        Kmm.diagonal().add_(self.jitter)                     # regressors.py:139 (K_mm_out) and :143 (K_mm_in_x)
-        S, Sinv = eng.sym_sqrt(Kmm, lambda_min_bound=self.jitter)
-        dev = dict(src=Zc, kernel=self.kernel, eng=eng, kind=kind, ls=ls, Z=Z, inv_ls=inv_ls, Kzz=Kzz, S=S, Sinv=Sinv)
+        dev = dict(src=Zc, kernel=self.kernel, eng=eng, kind=kind, ls=ls, Z=Z, inv_ls=inv_ls, Kzz=None, S=None, Sinv=None)
+        if landmark_stage:
+            self._landmark_stage(dev)
         self.__dict__["_dev"] = dev
         return dev
+
+    def _landmark_stage(self, dev):
+        """K_zz (regressors.py:144), K_mm = K_zz + jitter I (:139,143), S = K_mm^(1/2) and S^-1 (:140,152-153,163): the part
+        of the fit that depends on the landmarks only."""
+        eng = dev["eng"]
+        Kzz = eng.kzz(dev["Z"], dev["inv_ls"], dev["kind"])
+        Kmm = Kzz.clone()
+        Kmm.diagonal().add_(self.jitter)
+        S, Sinv = eng.sym_sqrt(Kmm, lambda_min_bound=self.jitter)
+        dev.update(Kzz=Kzz, S=S, Sinv=Sinv)
 
     # -- landmarks --------------------------------------------------------------------------------
     def _ensure_centers(self, Y_rows_getter, n):
@@ -264,11 +274,16 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         G = eng.gram_finalize()
         self._solve(eng, dev, G, n, d)
 
-    def fit_distributed(self, X_local, Y_local, group=None):
+    def fit_distributed(self, X_local, Y_local, group=None, head_rank=0):
         """Sample-sharded fit: every rank holds a contiguous block of samples; landmarks are drawn with
         the reference's call over the GLOBAL sample index (all ranks must share the numpy global RNG state), the
-        local Grams are summed with ONE allreduce, and every rank then solves redundantly (identical results)."""
+        local Grams are summed with ONE allreduce, and every rank then solves redundantly (identical results).
+
+        The landmark-only stage (K_zz, the symmetric square root S and S^-1) is computed by ``head_rank`` alone, after its
+        own Gram pass, and broadcast -- the other ranks are still streaming samples then if the head's shard is smaller by
+        ``sharding.head_samples(m, d, p)`` (see ``sharding.balanced_bounds``).  ``head_rank=None``: every rank computes it."""
         import torch
+        import torch.distributed as dist
         from . import sharding
         eng = _engine()
         n_local = int(X_local.shape[0])
@@ -280,10 +295,22 @@ class KoopmanNystromRegressor(KoopmanRegressor):
             Z = sharding.assemble_landmarks(idx, off, n_local, rows_of, d, group, eng.tdev)
             self.nystrom_centers_output = np.ascontiguousarray(Z.cpu().numpy().T)
         self._ensure_centers(None, n_total)
-        dev = self._device_state(d)
+        world = dist.get_world_size(group)
+        split = head_rank is not None and world > 1
+        dev = self._device_state(d, landmark_stage=not split)
         self._accumulate_grams(eng, dev, X_local, Y_local)
         G = eng.gram_finalize()
-        sharding.allreduce_grams(G["_flat"], group)                               # the only data-path collective
+        if split and dev.get("S") is None:
+            m = dev["Z"].shape[0]
+            lm = torch.empty(3, m, m, dtype=torch.float64, device=eng.tdev)
+            if dist.get_rank(group) == head_rank:
+                self._landmark_stage(dev)
+                lm[0].copy_(dev["Kzz"]); lm[1].copy_(dev["S"]); lm[2].copy_(dev["Sinv"])
+            sharding.allreduce_grams(G["_flat"], group)                           # the only data-path collective
+            dist.broadcast(lm, src=dist.get_global_rank(group, head_rank) if group is not None else head_rank, group=group)
+            dev.update(Kzz=lm[0], S=lm[1], Sinv=lm[2])
+        else:
+            sharding.allreduce_grams(G["_flat"], group)
         self._solve(eng, dev, G, n_total, d)
 
     def fit_cv(self, X, Y, kernels, gammas, n_splits=5, refit=True):

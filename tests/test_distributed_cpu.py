@@ -131,3 +131,20 @@ def test_cv_weight_exchange_world2():
         p_.join(timeout=120)
         assert p_.exitcode == 0
     assert out.get(timeout=5)
+
+
+def test_balanced_bounds_give_the_head_rank_a_shorter_block():
+    from nys_koop_lqr_b200 import sharding
+    h = sharding.head_samples(4096, 192, 6)
+    assert 50_000 < h < 80_000                       # measured on B200: 143 ms of landmark-only work ~ 66 k samples of Gram work
+    for n, w, head, hr in ((10_000_000, 8, h, 0), (10_000_000, 2, h, 0), (1003, 4, 100, 2), (50, 4, 1000, 0), (7, 1, 3, 0)):
+        spans = [sharding.balanced_bounds(n, w, r, head, hr) for r in range(w)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+        for (o1, c1), (o2, _) in zip(spans, spans[1:]):
+            assert o1 + c1 == o2 and c1 >= 0
+        if w > 1 and (n + head) // w - head >= 1:
+            others = [c for r, (_, c) in enumerate(spans) if r != hr]
+            assert max(others) - min(others) <= 1
+            assert abs((spans[hr][1] + head) - others[0]) <= 1      # equal total work
+        else:
+            assert spans == [sharding.shard_bounds(n, w, r) for r in range(w)]
