@@ -68,6 +68,14 @@ class Engine:
     def empty(self, *shape):
         return torch.empty(*shape, dtype=torch.float64, device=self.tdev)
 
+    def pinned_staging(self, count):
+        """Grow-only pinned host buffer of at least `count` doubles for device->host result copies."""
+        buf = getattr(self, "_pinned", None)
+        if buf is None or buf.numel() < count:
+            buf = torch.empty(int(count), dtype=torch.float64, pin_memory=True)
+            self._pinned = buf
+        return buf
+
     def launch_count(self) -> int:
         return int(self.lib.nk_launch_count(self.h))
 

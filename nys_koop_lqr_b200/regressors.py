@@ -245,7 +245,8 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         gamma_n = float(self.gamma) * float(n_total)                 # regressors.py:127
         A, B, C, W = eng.solve_abc(G, dev["Kzz"], dev["S"], dev["Sinv"], gamma_n, self.jitter)
         dev["W"] = W
-        host = torch.empty(A.numel() + B.numel() + C.numel() + W.numel(), dtype=torch.float64, pin_memory=True)
+        total = A.numel() + B.numel() + C.numel() + W.numel()
+        host = eng.pinned_staging(total)                             # grow-only pinned buffer owned by the engine (cudaHostAlloc is slow)
         o = 0
         outs = []
         for t in (A, B, C, W):
@@ -255,7 +256,7 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         torch.cuda.current_stream(eng.tdev).synchronize()
         arr = host.numpy()
         self.A, self.B, self.C, self.weights = (arr[o:o + int(np.prod(s))].reshape(tuple(s)).copy() for o, s in outs)
-        self._d2h_bytes = int(host.numel()) * 8
+        self._d2h_bytes = int(total) * 8
 
     # -- public API -------------------------------------------------------------------------------
     def fit(self, X, Y):

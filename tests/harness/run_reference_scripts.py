@@ -296,6 +296,12 @@ def run_cloth(rep, quick):
     cl = {w: mods[w].lqr_control(60, reference, init, pair[w], K[w]) for w in ("ref", "b200")}
     rep.add("cloth", "LQR seed=0 m=100", "closed-loop lifted rollout x over 60 steps", relerr(cl["b200"][0], cl["ref"][0]),
             relerr(mods["ref"].lqr_control(60, reference, init, pair["ref_perm"], Kf)[0], cl["ref"][0]))
+    # the batched device closed loop (nk_closed_loop) against the script's own numpy loop on the SAME fitted model and gain:
+    # isolates the kernel from the solver-algorithm gap above
+    states, ctrls = pair["b200"].closed_loop(K["b200"], init, reference, 60)
+    xs_script = cl["b200"][0]                                   # (64, 61): x coordinates incl. the initial state
+    rep.add("cloth", "LQR seed=0 m=100", "device closed loop (nk_closed_loop) vs the script's loop, same model: x over 60 steps",
+            relerr(states[0::3, :], xs_script[:, 1:]))
 
 
 # ------------------------------------------------------------------------------------------- HJB
