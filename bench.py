@@ -294,7 +294,9 @@ def run_gpu_arm(args):
                          "algorithmic_flops_per_sample": F, "samples_per_launch": float(np.mean(k_n)) if k_n else None,
                          "peak_source": "register-only DMMA.8x8x4 issue-rate probe (nk_probe_dmma_tflops) run on this GPU just before the timed region; "
                                         "MEASURED_PEAKS.json has no FP64 entry; cuBLAS DGEMM 8192^3 on this pool: 35.4 TFLOP/s, nominal 40",
-                         "whole_fit_frac": F * n / world / (ms_step * 1e-3) * 1e-12 / peak_tflops, "traffic_note": tnote},
+                         "whole_fit_frac": F * n / world / (ms_step * 1e-3) * 1e-12 / peak_tflops, "traffic_note": tnote,
+                         "peak_nominal": 40.0, "frac_nominal": (achieved / 40.0) if achieved else None,
+                         "nominal_note": "NVIDIA's B200 FP64 tensor figure (40 TFLOP/s); the DMMA issue rate measured on this pool is 37.1"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "model_check": {"A_shape": list(reg.A.shape), "A_fro": float(np.linalg.norm(reg.A)), "finite": bool(np.isfinite(reg.A).all() and np.isfinite(reg.C).all())},
         }
