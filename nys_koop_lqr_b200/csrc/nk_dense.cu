@@ -142,6 +142,33 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_kernel(GemmArgs g) {
     cp_async_wait<0>();
 
     const int gq = lane >> 2, t = lane & 3;
+    // plain alpha/beta update of a row-major, 16-byte aligned C: one 16-byte load and store per fragment pair
+    if (g.epi_kind < 0 && (g.flags & (kGemmMirror | kGemmStoreT | kGemmPackedOut)) == 0 && g.C != nullptr && (g.ldc % 2 == 0) &&
+        (g.sC % 2 == 0) && (((uintptr_t)g.C) % 16 == 0)) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int r = I * kTile + wr * 64 + i * 8 + gq;
+            if (r >= g.M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int c0 = J * kTile + wc * 32 + j * 8 + 2 * t;
+                if (c0 >= g.N) continue;
+                double *o = g.C + (long long)r * g.ldc + c0;
+                double v0 = g.alpha * acc[i][j][0], v1 = g.alpha * acc[i][j][1];
+                if (c0 + 1 < g.N) {
+                    if (g.beta != 0.0) { const double2 old = *reinterpret_cast<const double2 *>(o); v0 += g.beta * old.x; v1 += g.beta * old.y; }
+                    if (r == c0) v0 += g.diag;
+                    if (r == c0 + 1) v1 += g.diag;
+                    *reinterpret_cast<double2 *>(o) = make_double2(v0, v1);
+                } else {
+                    if (g.beta != 0.0) v0 += g.beta * o[0];
+                    if (r == c0) v0 += g.diag;
+                    o[0] = v0;
+                }
+            }
+        }
+        return;
+    }
     const bool mirror = (g.flags & kGemmMirror) != 0;   // symmetric result: element (r,c), r >= c, is also written to (c,r)
 #pragma unroll
     for (int i = 0; i < 8; i++) {
