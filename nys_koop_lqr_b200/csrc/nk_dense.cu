@@ -553,26 +553,10 @@ int potrf_blocked(nk_handle *h, int n, double *A, long long lda, double *Lt, lon
 }
 
 // ---- triangular solves in transposed storage (Xt rows = right-hand sides) ----
-// left-looking (gathers; r large):  block i of the unknown is a product over all earlier blocks
-void trsm_fwd_t(nk_handle *h, int n, int r, const double *L, long long ldl, const double *dinv, double *Xt, long long ldx, cudaStream_t stream) {
-    const int nblk = (n + kDB - 1) / kDB;
-    for (int i = 0; i < nblk; i++) {
-        const int j0 = i * kDB, nb = (n - j0 < kDB) ? n - j0 : kDB;
-        if (i > 0) gemm_nt(h, r, nb, j0, -1.0, Xt, ldx, L + (long long)j0 * ldl, ldl, 1.0, Xt + j0, ldx, 0.0, 0, nullptr, 0, stream);
-        gemm_nt(h, r, nb, nb, 1.0, Xt + j0, ldx, dinv + (size_t)i * kDB * kDB, kDB, 0.0, Xt + j0, ldx, 0.0, 0, nullptr, 0, stream);
-    }
-}
-void trsm_bwd_t(nk_handle *h, int n, int r, const double *Lt, long long ldlt, const double *dinvT, double *Xt, long long ldx, cudaStream_t stream) {
-    const int nblk = (n + kDB - 1) / kDB;
-    for (int i = nblk - 1; i >= 0; i--) {
-        const int j0 = i * kDB, nb = (n - j0 < kDB) ? n - j0 : kDB, j1 = j0 + nb;
-        if (j1 < n) gemm_nt(h, r, nb, n - j1, -1.0, Xt + j1, ldx, Lt + (long long)j0 * ldlt + j1, ldlt, 1.0, Xt + j0, ldx, 0.0, 0, nullptr, 0, stream);
-        gemm_nt(h, r, nb, nb, 1.0, Xt + j0, ldx, dinvT + (size_t)i * kDB * kDB, kDB, 0.0, Xt + j0, ldx, 0.0, 0, nullptr, 0, stream);
-    }
-}
-// right-looking, batched (scatters; few right-hand sides): once block i of the unknown is known, all later
-// (forward) / earlier (backward) blocks are updated by one wide product -> (n / 128) CTAs per launch even when r is small.
-// sL / sD / sX = 0 shares the factor / right-hand sides across the batch.
+// Right-looking, batched: once block i of the unknown is known, all later (forward) / earlier (backward) blocks are
+// updated by one wide product -> (r / 128) x (n / 128) CTAs per launch.  (The first version was left-looking -- block i as
+// one product over all earlier blocks -- which launches only r / 128 CTAs at a time: 32 of 148 SMs busy at m = 4096, and
+// 55 of the 88 ms of a fit's solve stage.)  sL / sD / sX = 0 shares the factor / right-hand sides across the batch.
 void trsm_fwd_t_rl(nk_handle *h, int batch, int n, int r, const double *L, long long ldl, long long sL, const double *dinv, long long sD,
                    double *Xt, long long ldx, long long sX, cudaStream_t stream) {
     constexpr int kOuter = 4 * kDB;      // same two-level blocking as potrf_batched: the bulk of the update runs with K = 512
@@ -606,6 +590,13 @@ void trsm_bwd_t_rl(nk_handle *h, int batch, int n, int r, const double *Lt, long
         if (p0 > 0) gemm_nt_batched(h, batch, r, p0, pend - p0, -1.0, Xt + p0, ldx, sX, Lt + p0, ldlt, sLt, 1.0, Xt, ldx, sX, 0.0, 0, nullptr, 0, 0,
                                     stream);
     }
+}
+
+void trsm_fwd_t(nk_handle *h, int n, int r, const double *L, long long ldl, const double *dinv, double *Xt, long long ldx, cudaStream_t stream) {
+    trsm_fwd_t_rl(h, 1, n, r, L, ldl, 0, dinv, 0, Xt, ldx, 0, stream);
+}
+void trsm_bwd_t(nk_handle *h, int n, int r, const double *Lt, long long ldlt, const double *dinvT, double *Xt, long long ldx, cudaStream_t stream) {
+    trsm_bwd_t_rl(h, 1, n, r, Lt, ldlt, 0, dinvT, 0, Xt, ldx, 0, stream);
 }
 
 double *dense_scratch(nk_handle *h, int slot, size_t doubles, int *rc) {
