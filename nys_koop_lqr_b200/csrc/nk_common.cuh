@@ -68,20 +68,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 __device__ __forceinline__ uint64_t policy_evict_last() {
     uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
 }
-__device__ __forceinline__ uint64_t policy_evict_first() {
-    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
-}
-__device__ __forceinline__ void red_add_f64(double *p, double v, uint64_t policy) {
-    asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(policy) : "memory");
-}
 __device__ __forceinline__ void st_v2_hint(double *p, double a, double b, uint64_t policy) {
     asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(a), "d"(b), "l"(policy) : "memory");
 }
 __device__ __forceinline__ int ld_acquire(const int *p) {
     int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
-}
-__device__ __forceinline__ void st_release(int *p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // register re-partitioning between warpgroups (sm_90a+): the producer warpgroup hands its registers to the consumers
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }

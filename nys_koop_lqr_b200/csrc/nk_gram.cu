@@ -23,7 +23,9 @@
 // CTA = 8 consumer warps (2 x 4, warp tile 64 x 32, 64 FP64 accumulators per lane) + 1 producer warp that
 // claims items one ahead, resolves their dependences and feeds a 3-stage ring of 2 x 16 KB operand slabs with
 // cp.async.bulk (TMA engine, mbarrier transaction counts); 128 KB of shared memory stage the accumulator tiles
-// for the asynchronous bulk reduce-add of the Gram epilogue.
+// for the asynchronous bulk reduce-add of the Gram epilogue and the exponents of the kernel-function epilogue.
+// Measured dead ends: two 4-warp CTAs per SM as a ping-pong (-1.5%: the 168-register budget
+// costs the cross-step fragment prefetch), spreading the fragment loads, more ILP in the kernel-function loop.
 #include "nk_gram.cuh"
 #include "nk_mainloop.cuh"
 
@@ -41,28 +43,6 @@ struct GramSmemCtl {
 
 __device__ __forceinline__ void spin_until_ge(const int *ctr, int target) {
     while (ld_acquire(ctr) < target) { __nanosleep(64); }
-}
-
-// ------------------------------------------------------------------------------------------------
-// consumer: one 16-deep slab of the 64x32 warp tile
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_mma_slab(double (&acc)[8][4][2], const double *As, const double *Bs, int wr, int wc, int lane) {
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-        double2 a[8], b[4];
-#pragma unroll
-        for (int i = 0; i < 8; i++) a[i] = *reinterpret_cast<const double2 *>(As + ((wr * 8 + i) * 2 + q) * kBlk + lane * 2);
-#pragma unroll
-        for (int j = 0; j < 4; j++) b[j] = *reinterpret_cast<const double2 *>(Bs + ((wc * 4 + j) * 2 + q) * kBlk + lane * 2);
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
