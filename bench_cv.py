@@ -4,6 +4,7 @@ landmarks, n=2e6 samples, 5 folds, then a 10^5-trajectory open-loop rollout of t
 
     python bench_cv.py                       # full configuration (about 8 minutes on one B200)
     python bench_cv.py --n 200000 --m 4096 --kernels 2 --traj 10000      # reduced, for a quick look
+    torchrun --nproc-per-node 8 bench_cv.py                               # samples and trajectories sharded over the GPUs
 
 Not the driver's headline bench (that is bench.py, configs[3]); this script measures the second synthetic configuration
 through the drop-in estimator's batched search (`fit_cv`) and `Engine.rollout`, and prints ONE JSON line.
@@ -27,8 +28,8 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=2_000_000)
-    ap.add_argument("--m", type=int, default=8192)
+    ap.add_argument("--samples", "--n", dest="n", type=int, default=2_000_000)
+    ap.add_argument("--landmarks", "--m", dest="m", type=int, default=8192)
     ap.add_argument("--d", type=int, default=192)
     ap.add_argument("--p", type=int, default=6)
     ap.add_argument("--kernels", type=int, default=16)
@@ -43,13 +44,24 @@ def main():
     from nys_koop_lqr_b200.engine import Engine
     if not torch.cuda.is_available():
         raise SystemExit("bench_cv.py: no CUDA device (no CPU fallback)")
-    dev = torch.device("cuda", 0)
+    import torch.distributed as dist
+    from nys_koop_lqr_b200 import sharding
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    eng = Engine.get(0)
-    n, m, d, p = args.n, args.m, args.d, args.p
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    eng = Engine.get(local_rank)
+    n_total, m, d, p = args.n, args.m, args.d, args.p
+    off, n = sharding.shard_bounds(n_total, world, rank)          # this rank's contiguous block of the samples
     g = torch.Generator(device=dev); g.manual_seed(1234)
     M = torch.randn(d, d, dtype=torch.float64, device=dev, generator=g) * (0.9 / d ** 0.5)
     Bu = 0.1 * torch.randn(d, p, dtype=torch.float64, device=dev, generator=g)
+    g.manual_seed(5000 + rank)
     X = torch.empty(n, d + p, dtype=torch.float64, device=dev)
     Y = torch.empty(n, d, dtype=torch.float64, device=dev)
     for s in range(0, n, 1 << 19):
@@ -64,24 +76,37 @@ def main():
     reg = R.KoopmanNystromRegressor(p, kernel=kernels[0], gamma=gammas[0], m=m)
     reg.cv_profile = True
     l0 = eng.launch_count()
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    res = reg.fit_cv(X, Y, kernels, gammas, n_splits=args.folds, refit=False)
-    torch.cuda.synchronize(); t_cv = time.perf_counter() - t0
-    prof = dict(reg.cv_profile_)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    barrier(); t0 = time.perf_counter()
+    if world > 1:
+        res = reg.fit_cv_distributed(X, Y, kernels, gammas, n_splits=args.folds, refit=False)
+    else:
+        res = reg.fit_cv(X, Y, kernels, gammas, n_splits=args.folds, refit=False)
+    barrier(); t_cv = time.perf_counter() - t0
+    prof = dict(reg.cv_profile_) if getattr(reg, "cv_profile_", None) else {"gram_s": float("nan"), "weights_s": float("nan"), "score_s": float("nan")}
     t0 = time.perf_counter()
     reg.kernel, reg.gamma = reg.best_params_["kernel"], reg.best_params_["gamma"]
-    reg.fit(X, Y)
-    torch.cuda.synchronize(); t_refit = time.perf_counter() - t0
+    if world > 1:
+        reg.fit_distributed(X, Y)
+    else:
+        reg.fit(X, Y)
+    barrier(); t_refit = time.perf_counter() - t0
     launches_cv = eng.launch_count() - l0
 
     # ---- rollout of the refitted model over many trajectories (replicas only: trajectories are independent) ----
-    nb, T = args.traj, args.T
+    nb_total, T = args.traj, args.T
+    nb = sharding.shard_bounds(nb_total, world, rank)[1]         # trajectories are independent: replicas only, no collective
+    n = n_total
     dv = reg._device_state(d)
     A, B, C = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (reg.A, reg.B, reg.C))
     x0 = X[:nb, :d].contiguous()
     U = torch.randn(T - 1, nb, p, dtype=torch.float64, device=dev, generator=g)
     Ytrue = torch.randn(T, nb, d, dtype=torch.float64, device=dev, generator=g)
-    torch.cuda.synchronize()
+    barrier()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     l1 = eng.launch_count()
     e0.record()
@@ -90,13 +115,18 @@ def main():
     out = eng.rollout(A, B, C, Z0, U, Ytrue=Ytrue, return_traj=False)
     e2.record(); torch.cuda.synchronize()
     ms_lift, ms_roll = e0.elapsed_time(e1), e1.elapsed_time(e2)
+    if world > 1:                                                 # device time, max over ranks
+        tt = torch.tensor([ms_lift, ms_roll], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_lift, ms_roll = float(tt[0]), float(tt[1])
+    nb = nb_total
     fl_roll = nb * ((T - 1) * (2.0 * m * m + 2.0 * m * p) + T * 2.0 * d * m)
     rmse = torch.sqrt(out["sq_err"] / (d * T))
 
     F = 4.0 * m * m + 6.0 * m * d + 4.0 * m * p
     n_solves = args.kernels * args.gammas * args.folds
     chol_flops = n_solves * (m ** 3 / 3.0 + (m + p) ** 3 / 3.0)
-    peak = eng.probe_dmma_tflops(200.0)
+    peak = eng.probe_dmma_tflops(200.0) * world
     line = {
         "config": {"workload": f"synthetic CV sweep {args.kernels} lengthscales x {args.gammas} gamma at m={m}, n={n}, d={d}, p={p}, "
                                f"{args.folds} folds + {nb}-trajectory rollout T={T} (BASELINE.json configs[4])",
@@ -114,9 +144,13 @@ def main():
         "dmma_peak_tflops": peak, "gpu_launches": int(launches_cv + (eng.launch_count() - l1)),
         "best": {"index": reg.best_index_, "lengthscale": float(ls[kernels.index(reg.best_params_["kernel"])]), "gamma": reg.best_params_["gamma"],
                  "score": reg.best_score_, "nan_candidates": int(np.isnan(res["mean_test_score"]).sum())},
-        "dtype": "f64", "data": "synthetic", "n_gpus": 1,
+        "dtype": "f64", "data": "synthetic", "n_gpus": world,
     }
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

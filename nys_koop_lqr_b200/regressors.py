@@ -420,11 +420,20 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         Z = torch.from_numpy(np.ascontiguousarray(np.asarray(self.nystrom_centers_output, dtype=np.float64).T)).to(eng.tdev)
         m, nlam = Z.shape[0], len(gammas)
         scores = np.full((len(kernels), nlam, n_splits), np.nan)
+        prof = {"gram_s": 0.0, "weights_s": 0.0, "score_s": 0.0} if getattr(self, "cv_profile", False) else None
+
+        def tick():
+            if prof is None:
+                return 0.0
+            import time
+            torch.cuda.synchronize(eng.tdev)
+            return time.perf_counter()
         for ki, holder in enumerate(kernels):
             kind, ls = kernel_spec(holder, d)
             inv_ls = torch.from_numpy(1.0 / ls).to(eng.tdev)
             Kzz = eng.kzz(Z, inv_ls, kind)
             stacked = None
+            t0 = tick()
             for fi, (lo, hi) in enumerate(local):
                 eng.gram_begin(Z, inv_ls, kind, p, self.gram_chunk)
                 if hi > lo:
@@ -434,6 +443,7 @@ class KoopmanNystromRegressor(KoopmanRegressor):
                     stacked = torch.empty(n_splits, flat.numel(), dtype=torch.float64, device=eng.tdev)
                 stacked[fi].copy_(flat)
             sharding.allreduce_sum(stacked, group)                                  # per-fold Grams of ALL samples
+            t1 = tick()
             Wall = torch.zeros(n_splits, nlam, d, m + p, dtype=torch.float64, device=eng.tdev)
             bad = torch.zeros(n_splits, nlam, dtype=torch.int32, device=eng.tdev)
             train = torch.empty_like(stacked[0])
@@ -453,17 +463,22 @@ class KoopmanNystromRegressor(KoopmanRegressor):
                 bad[fi, g0:g1] = torch.as_tensor(info, dtype=torch.int32, device=eng.tdev)
             sharding.allreduce_sum(Wall, group)                                     # every slice was written by exactly one rank
             sharding.allreduce_sum(bad, group)
+            t2 = tick()
             sse = torch.zeros(n_splits, nlam, d, dtype=torch.float64, device=eng.tdev)
             for fi, (lo, hi) in enumerate(local):
                 if hi > lo:
                     eng.cv_score(Z, inv_ls, kind, Wall[fi], Xd[lo:hi], Yd[lo:hi], p, sse=sse[fi])
             sharding.allreduce_sum(sse, group)
             sse_h, bad_h = sse.cpu().numpy(), bad.cpu().numpy()
+            if prof is not None:
+                t3 = tick()
+                prof["gram_s"] += t1 - t0; prof["weights_s"] += t2 - t1; prof["score_s"] += t3 - t2
             for fi, (s, e) in enumerate(folds):
                 sc = -np.mean(np.sqrt(sse_h[fi] / (e - s)), axis=1)
                 sc[bad_h[fi] != 0] = np.nan
                 scores[ki, :, fi] = sc
             del stacked, Wall, train
+        self.cv_profile_ = prof
         return self._finish_cv(scores, kernels, gammas, n_splits, refit,
                                lambda: self.fit_distributed(Xd, Yd, group=group))
 
