@@ -97,9 +97,18 @@ def cpu_rate(n_sample, m, d, p, seed=0):
     np.random.seed(0)
     Z = O.draw_landmarks(Y, m)
     Xs, U, Y = Xs[:n_sample], U[:n_sample], Y[:n_sample]
-    t0 = time.perf_counter()
-    O.grams(Xs, Y, U, Z, O.RBF, np.full(d, 10.0), chunk=n_sample)
-    dt = time.perf_counter() - t0
+    # all host threads for the BLAS part, also when a launcher (torchrun) exported OMP_NUM_THREADS=1 before numpy was loaded;
+    # scipy's cdist is single-threaded by construction, exactly as in the reference
+    try:
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(limits=os.cpu_count())
+    except Exception:  # noqa: BLE001
+        import contextlib
+        ctx = contextlib.nullcontext()
+    with ctx:
+        t0 = time.perf_counter()
+        O.grams(Xs, Y, U, Z, O.RBF, np.full(d, 10.0), chunk=n_sample)
+        dt = time.perf_counter() - t0
     return n_sample / dt, dt
 
 
@@ -270,7 +279,7 @@ def run_gpu_arm(args):
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:           # the CPU baseline is reported at N=1 only
             r, dt = cpu_rate(args.cpu_sample, m, d, p)
             cpu = {"value": r, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                    "sample": f"{args.cpu_sample} samples at m={m}, d={d}: n-proportional stage of the reference fit (scipy cdist lift + Gram dgemms) "
