@@ -90,3 +90,30 @@ def test_rollout_linearity_at_large_m(engine):
         if i < T - 1:
             z = z @ A.T + (Ua + Ub)[i, :64] @ B.T
     assert float((yab["Zfinal"][:64] - z).norm() / z.norm()) <= 1e-12
+
+
+def test_dense_stage_residuals_at_large_m(engine):
+    """Blocked Cholesky (two-level, 9 panels), triangular solves and the symmetric square root at m=4096+37 on a real kernel
+    matrix: residual identities instead of a CPU comparison (LAPACK would take minutes here)."""
+    m, d = 4096 + 37, 24
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev); g.manual_seed(11)
+    Z = torch.randn(m, d, dtype=torch.float64, device=dev, generator=g)
+    il = torch.full((d,), 1.0 / 3.0, dtype=torch.float64, device=dev)
+    K = engine.kzz(Z, il, 0)
+    K.diagonal().add_(1e-6)
+    nrm = float(K.norm())
+    L = engine.potrf(K.clone())
+    assert float((L @ L.T - K).norm()) <= 1e-14 * nrm * 10
+    assert float(torch.triu(L, 1).abs().max()) == 0.0
+    # triangular solves: L (L^-1 B) == B, L^T (L^-T B) == B
+    B = torch.randn(m, 130, dtype=torch.float64, device=dev, generator=g)
+    Y1 = engine.trsm_lower(L, B.clone(), trans=False)
+    assert float((L @ Y1 - B).norm() / B.norm()) <= 1e-10
+    Y2 = engine.trsm_lower(L, B.clone(), trans=True)
+    assert float((L.T @ Y2 - B).norm() / B.norm()) <= 1e-10
+    S, Sinv = engine.sym_sqrt(K, 1e-6)
+    assert float((S @ S - K).norm()) <= 1e-12 * nrm
+    assert float((S - S.T).abs().max()) == 0.0 and float((Sinv - Sinv.T).abs().max()) == 0.0
+    eye = torch.eye(m, dtype=torch.float64, device=dev)
+    assert float((Sinv @ K @ Sinv - eye).norm() / eye.norm()) <= 1e-8       # S^-1 K S^-1 = I, amplified by cond(K) ~ 1e9 * eps
