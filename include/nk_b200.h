@@ -56,6 +56,11 @@ int nk_probe_dmma_tflops(nk_handle *h, double ms_target, double *tflops);
 int nk_kzz(nk_handle *h, const double *Z, long long ldz, int m, int d, const double *inv_ls, int kind,
            double *Kzz, long long ldk, void *stream);
 
+/* ---- the kernel function itself, elementwise: out[i] = k(exponent[i]) where exponent = -r^2/2 of the length-scaled distance r
+ * (what the lift GEMMs accumulate): RBF exp(-r^2/2) (sklearn kernels.py RBF.__call__), Matern-5/2 (1+a+a^2/3)exp(-a), a=sqrt(5) r
+ * (Matern.__call__, nu=2.5).  Exposed so that the device implementation can be checked against the library functions. ---- */
+int nk_kernel_function(nk_handle *h, int kind, long long count, const double *exponent, double *out, void *stream);
+
 /* ---- kernel cross matrix K = k(Z, X): (m, N) row-major from X (N, d) rows  (regressors.py:176) ---- */
 int nk_kernel_cross(nk_handle *h, const double *Z, long long ldz, int m, int d, const double *inv_ls, int kind,
                     const double *X, long long ldx, long long N, double *K, long long ldk, void *stream);

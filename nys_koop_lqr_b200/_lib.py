@@ -30,6 +30,7 @@ _SIGNATURES = {
     "nk_gram_last_executed_flops": ([C.c_void_p], _d),
     "nk_launch_count": ([C.c_void_p], _ll),
     "nk_probe_dmma_tflops": ([C.c_void_p, _d, C.POINTER(_d)], _i),
+    "nk_kernel_function": ([C.c_void_p, _i, _ll, _c_dp, _c_dp, C.c_void_p], _i),
     "nk_kzz": ([C.c_void_p, _c_dp, _ll, _i, _i, _c_dp, _i, _c_dp, _ll, C.c_void_p], _i),
     "nk_kernel_cross": ([C.c_void_p, _c_dp, _ll, _i, _i, _c_dp, _i, _c_dp, _ll, _ll, _c_dp, _ll, C.c_void_p], _i),
     "nk_gemm": ([C.c_void_p, _i, _i, _i, _i, _i, _d, _c_dp, _ll, _c_dp, _ll, _d, _c_dp, _ll, C.c_void_p], _i),

@@ -81,6 +81,10 @@ __global__ void sse_columns_kernel(long long rows, int R, int d, const double *Y
     }
 }
 
+__global__ void kernel_function_kernel(long long n, int kind, const double *e, double *out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = kernel_from_exponent(e[i], kind);
+}
+
 int kernel_cross_t(nk_handle *h, const double *Z, long long ldz, int m, int d, const double *inv_ls, int kind,
                    const double *X, long long ldx, long long N, double *Kt, long long ldkt, cudaStream_t stream, int packed_rp);
 void copy_cols(nk_handle *h, long long rows, int cols, const double *src, long long lds, double *dst, long long ldd, cudaStream_t stream);
@@ -90,6 +94,18 @@ void copy_cols(nk_handle *h, long long rows, int cols, const double *src, long l
 using namespace nk;
 
 extern "C" {
+
+int nk_kernel_function(nk_handle *h, int kind, long long count, const double *exponent, double *out, void *stream_) {
+    if (!h) return NK_E_INVALID;
+    if (count < 0 || !exponent || !out || (kind != NK_KERNEL_RBF && kind != NK_KERNEL_MATERN52)) return set_err(h, NK_E_INVALID, "nk_kernel_function: bad argument");
+    if (count == 0) return NK_OK;
+    NK_CUDA(h, cudaSetDevice(h->device));
+    const long long blocks = (count + 255) / 256;
+    kernel_function_kernel<<<(unsigned)(blocks < 8192 ? blocks : 8192), 256, 0, (cudaStream_t)stream_>>>(count, kind, exponent, out);
+    h->launches++;
+    NK_CUDA(h, cudaGetLastError());
+    return NK_OK;
+}
 
 int nk_axpy(nk_handle *h, long long count, double alpha, const double *x, double *y, void *stream_) {
     if (!h) return NK_E_INVALID;

@@ -152,6 +152,13 @@ class Engine:
         return float(self.lib.nk_gram_last_executed_flops(self.h))
 
     # ------------------------------------------------------------------ dense stage
+    def kernel_function(self, exponent, kind):
+        """Elementwise kernel function of an array of exponents -r^2/2 (device implementation used by every lift)."""
+        _f64(exponent, "exponent")
+        out = torch.empty_like(exponent)
+        self._ck(self.lib.nk_kernel_function(self.h, int(kind), exponent.numel(), _ptr(exponent), _ptr(out), self._stream()), "nk_kernel_function")
+        return out
+
     def kzz(self, Z, inv_ls, kind):
         m, d = Z.shape
         K = self.empty(m, m)

@@ -275,3 +275,24 @@ def test_closed_loop_against_reference_loop(engine, m, p, d, nb, steps):
         xs, us = O.closed_loop(A, B, Cm, K, z0[b], zr[b], steps)
         assert O.relerr(Xs[:, b, :].T, xs) <= 1e-11
         assert O.relerr(Us[:, b, :].T, us) <= 1e-11
+
+
+def test_kernel_function_accuracy(engine):
+    """The device kernel function (nk_kernel_function: what every lift epilogue evaluates) against numpy on 2e6 exponents spanning
+    the whole range, including the denormal tail and exact underflow: <= 2 ulp for normal results, absolute 1e-320 below."""
+    rng = np.random.default_rng(0)
+    e = -np.concatenate([rng.uniform(0, 40, 1_000_000), 10.0 ** rng.uniform(-12, 2.9, 900_000), rng.uniform(700, 760, 100_000),
+                         [0.0, 1e-300, 708.0, 745.0, 746.0, 2000.0, 1e300]])
+    got = host(engine.kernel_function(dev(e), O.RBF))
+    want = np.exp(e)
+    normal = want > 1e-300
+    ulp = np.abs(got[normal] - want[normal]) / np.spacing(want[normal])
+    assert ulp.max() <= 2.0, ulp.max()
+    assert np.abs(got[~normal] - want[~normal]).max() <= 1e-300 * 1e-15 + 1e-320
+    assert got[-7] == 1.0 and got[-2] == 0.0 and got[-1] == 0.0
+    # Matern-5/2: (1 + a + a^2/3) exp(-a), a = sqrt(5) r, exponent = -r^2/2
+    r = rng.uniform(0, 30, 200_000)
+    gm = host(engine.kernel_function(dev(-0.5 * r * r), O.MATERN52))
+    a = np.sqrt(5.0) * r
+    wm = (1.0 + a + a * a / 3.0) * np.exp(-a)
+    assert (np.abs(gm - wm) / wm).max() <= 1e-14        # r is recovered from -r^2/2: a few ulp of a in the exponent
