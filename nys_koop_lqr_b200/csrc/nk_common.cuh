@@ -32,6 +32,17 @@ __host__ __device__ inline size_t packed_off(int r, int k, int row_panels) {
     return ((size_t)(k >> 4) * row_panels + (r >> 3)) * 128 + ((k & 15) >> 3) * 64 + (r & 7) * 8 + (k & 7);
 }
 
+// Kernel attributes (opt-in dynamic shared memory) are per DEVICE: remember per device ordinal which kernels were configured,
+// so that one process driving several GPUs (one handle each) configures each of them.
+inline bool first_use_on_device(unsigned long long &mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
+
 // ---- PTX wrappers -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -209,11 +209,10 @@ void gemm_nt_batched(nk_handle *h, int batch, int M, int N, int K, double alpha,
                      const double *B, long long ldb, long long sB, double beta, double *C, long long ldc, long long sC, double diag,
                      int flags, double *Ct, long long ldct, long long sCt, cudaStream_t stream, int epi_kind) {
     if (M <= 0 || N <= 0 || batch <= 0) return;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;
+    if (first_use_on_device(configured)) {
         cudaFuncSetAttribute(gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
         cudaFuncSetAttribute(gemm_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
-        configured = true;
     }
     GemmArgs g;
     g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.diag = diag;
@@ -475,8 +474,8 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double *A_, long lon
 
 static void launch_diag(nk_handle *h, int batch, double *A, long long lda, long long sA, int nb, int j0, double *dinv, double *dinvT,
                         long long sD, int *dinfo, int do_factor, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) { cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem); configured = true; }
+    static unsigned long long configured = 0;
+    if (first_use_on_device(configured)) cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem);
     potrf_diag_kernel<<<batch, 256, kDiagSmem, stream>>>(A, lda, sA, nb, j0, dinv, dinvT, sD, dinfo, do_factor);
     h->launches++;
 }

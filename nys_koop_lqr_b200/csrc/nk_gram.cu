@@ -399,11 +399,10 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
 }
 
 void launch_gram(const GramParams &P, int sm_count, cudaStream_t stream, cudaError_t *err) {
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;
+    if (first_use_on_device(configured)) {
         *err = cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGramSmemBytes);
         if (*err != cudaSuccess) return;
-        configured = true;
     }
     // every CTA must be resident (items wait on items claimed earlier): cooperative launch guarantees it
     int max_blocks = 0;

@@ -156,8 +156,8 @@ __global__ void __launch_bounds__(kThreads, 1) pgemm_kernel(const PGemmParams P)
 }
 
 void launch_pgemm(nk_handle *h, const PGemmParams &P, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) { cudaFuncSetAttribute(pgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPgSmemBytes); configured = true; }
+    static unsigned long long configured = 0;
+    if (first_use_on_device(configured)) cudaFuncSetAttribute(pgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPgSmemBytes);
     const int n_tiles = P.tiles_m * P.tiles_n;
     if (n_tiles <= 0 || P.KS <= 0) return;
     const int grid = n_tiles < h->sm_count ? n_tiles : h->sm_count;

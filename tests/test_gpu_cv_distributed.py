@@ -57,3 +57,30 @@ def test_fit_cv_distributed_world2_matches_gridsearchcv_golden():
     got = sorted(out.get(timeout=5) for _ in range(2))
     for rank, rel, best_ok, errA in got:
         assert rel <= 1e-8 and best_ok and errA <= 1e-7, (rank, rel, best_ok, errA)
+
+
+def test_two_devices_in_one_process():
+    """One process, two handles (one per GPU): every kernel's opt-in shared-memory attribute is configured per device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from nys_koop_lqr_b200.engine import Engine
+    from oracle import nk_oracle as O
+    rng = np.random.default_rng(0)
+    n, d, p, m = 700, 5, 2, 40
+    Xs, U, Y = O.synthetic(n, d, p, seed=3)
+    Z = Y[rng.choice(n, m, replace=False)]
+    ls = np.full(d, 2.0)
+    ref = O.grams(Xs, Y, U, Z, O.RBF, ls)
+    for devno in (0, 1):
+        eng = Engine.get(devno)
+        with torch.cuda.device(devno):
+            t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=f"cuda:{devno}")
+            G = eng.grams(t(np.hstack((Xs, U))), t(Y), t(Z), t(1.0 / ls), O.RBF, p)
+            assert O.relerr(G["Gyx"].cpu().numpy(), ref["Gyx"]) <= 1e-12
+            K = eng.kzz(t(Z), t(1.0 / ls), O.RBF)
+            K.diagonal().add_(1e-6)
+            S, Sinv = eng.sym_sqrt(K)
+            assert float((S @ S - K).norm() / K.norm()) <= 1e-12
+            z0 = t(rng.standard_normal((3, m)))
+            out = eng.rollout(t(rng.standard_normal((m, m)) * 0.1), None, t(rng.standard_normal((d, m))), z0, None, Ytrue=t(rng.standard_normal((1, 3, d))))
+            assert out["Yhat"].shape == (1, 3, d)
