@@ -27,6 +27,10 @@ int nk_create(nk_handle **out, int device);
 int nk_destroy(nk_handle *h);
 const char *nk_last_error_string(nk_handle *h);   /* h may be NULL: last creation error */
 int nk_device_sm_count(nk_handle *h);
+/* Workspaces are grow-only per handle (a CV sweep at m=8192 leaves tens of GB behind): this frees all of them (synchronises
+ * the device; the next call reallocates what it needs).  A Gram accumulation in progress is discarded (nk_gram_update /
+ * nk_gram_finalize then fail with NK_E_STATE until the next nk_gram_begin). */
+int nk_release_scratch(nk_handle *h);
 
 /* ---- fused kernel lift + data-sample Grams  (regressors.py:141-142 lift; :147,151,153,162,164 Grams) ----
  * Streaming form: begin(landmarks, kernel) -> update(sample block)* -> finalize(outputs).

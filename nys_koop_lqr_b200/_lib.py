@@ -24,6 +24,7 @@ _SIGNATURES = {
     "nk_destroy": ([C.c_void_p], _i),
     "nk_last_error_string": ([C.c_void_p], C.c_char_p),
     "nk_device_sm_count": ([C.c_void_p], _i),
+    "nk_release_scratch": ([C.c_void_p], _i),
     "nk_gram_begin": ([C.c_void_p, _c_dp, _ll, _i, _i, _i, _c_dp, _i, _i, C.c_void_p], _i),
     "nk_gram_update": ([C.c_void_p, _c_dp, _ll, _c_dp, _ll, _ll, C.c_void_p], _i),
     "nk_gram_finalize": ([C.c_void_p] + [_c_dp, _ll] * 7 + [_i, C.c_void_p], _i),

@@ -92,6 +92,18 @@ int nk_destroy(nk_handle *h) {
     return NK_OK;
 }
 
+int nk_release_scratch(nk_handle *h) {
+    if (!h) return NK_E_INVALID;
+    h->gram_open = false;      // an accumulation in progress is discarded: nk_gram_update / _finalize need a new nk_gram_begin
+    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_CUDA(h, cudaDeviceSynchronize());
+    nk_devbuf *bufs[] = {&h->zp, &h->inv_ls, &h->center, &h->xp[0], &h->xp[1], &h->yp[0], &h->yp[1], &h->psi[0], &h->psi[1],
+                         &h->gws, &h->items, &h->counters, &h->tile_of, &h->dinfo};
+    for (nk_devbuf *b : bufs) if (b->ptr) { cudaFree(b->ptr); b->ptr = nullptr; b->bytes = 0; }
+    for (nk_devbuf &b : h->dense) if (b.ptr) { cudaFree(b.ptr); b.ptr = nullptr; b.bytes = 0; }
+    return NK_OK;
+}
+
 const char *nk_last_error_string(nk_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 int nk_device_sm_count(nk_handle *h) { return h ? h->sm_count : 0; }
 double nk_gram_last_executed_flops(nk_handle *h) { return h ? h->last_flops : 0.0; }

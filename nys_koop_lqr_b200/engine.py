@@ -68,6 +68,11 @@ class Engine:
     def empty(self, *shape):
         return torch.empty(*shape, dtype=torch.float64, device=self.tdev)
 
+    def release_scratch(self):
+        """Free the handle's grow-only device workspaces (and the pinned staging buffer)."""
+        self._ck(self.lib.nk_release_scratch(self.h), "nk_release_scratch")
+        self._pinned = None
+
     def pinned_staging(self, count):
         """Grow-only pinned host buffer of at least `count` doubles for device->host result copies."""
         buf = getattr(self, "_pinned", None)

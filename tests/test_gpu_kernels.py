@@ -296,3 +296,18 @@ def test_kernel_function_accuracy(engine):
     a = np.sqrt(5.0) * r
     wm = (1.0 + a + a * a / 3.0) * np.exp(-a)
     assert (np.abs(gm - wm) / wm).max() <= 1e-14        # r is recovered from -r^2/2: a few ulp of a in the exponent
+
+
+def test_release_scratch(engine):
+    """Workspaces can be dropped and are rebuilt on demand; an accumulation in progress is discarded loudly."""
+    from nys_koop_lqr_b200._lib import NkError
+    Xs, U, Y, Z = make_problem(500, 4, 1, 30, seed=1)
+    lsv = np.full(4, 2.0)
+    Xa, Yd, Zd, il = dev(np.hstack((Xs, U))), dev(Y), dev(Z), dev(1.0 / lsv)
+    G1 = engine.grams(Xa, Yd, Zd, il, O.RBF, 1)
+    engine.gram_begin(Zd, il, O.RBF, 1)
+    engine.release_scratch()
+    with pytest.raises(NkError):
+        engine.gram_update(Xa, Yd)
+    G2 = engine.grams(Xa, Yd, Zd, il, O.RBF, 1)
+    assert torch.equal(G1["_flat"], G2["_flat"])
