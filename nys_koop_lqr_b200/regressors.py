@@ -614,12 +614,14 @@ KoopmanNystromRegressor.closed_loop = _closed_loop
 
 # ----------------------------------------------------------------------------------------------
 # out-of-scope baselines (regressors.py:58-111 exact-kernel, :181-234 thin-plate splines): not part of the B200
-# hot path.  They are re-exported from an upstream checkout when one is reachable so that the
-# scripts' `from regressors import *` keeps working; otherwise instantiating them explains what to do.
+# hot path.  They are re-exported from an upstream checkout only when NK_REFERENCE_PATH names one (so
+# that the scripts' spline comparisons keep working); otherwise instantiating them explains what to do.
 # ----------------------------------------------------------------------------------------------
 def _load_upstream():
-    root = pathlib.Path(os.environ.get("NK_REFERENCE_PATH", "/root/reference"))
-    f = root / "regressors.py"
+    root = os.environ.get("NK_REFERENCE_PATH")       # opt-in only: the product never looks for a reference tree on its own
+    if not root:
+        return None
+    f = pathlib.Path(root) / "regressors.py"
     if not f.exists():
         return None
     spec = importlib.util.spec_from_file_location("_nk_upstream_regressors", f)
