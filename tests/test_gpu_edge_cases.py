@@ -1,0 +1,93 @@
+"""GPU edge cases of the estimator path (through the drop-in class and the C ABI) against the oracle: degenerate sizes
+(one landmark, one state dimension, no controls, fewer samples than one tile), landmarks that coincide (K_mm singular but for
+the 1e-6 jitter of regressors.py:139), samples that coincide with landmarks (r = 0 inside the lift), sample counts around the
+128-sample strip and 512-sample chunk edges, and an empty sample block inside a streamed accumulation.
+"""
+import numpy as np
+import pytest
+
+from oracle import nk_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _fit_pair(n, d, p, m, kind, ls, gamma, seed=0, Z=None):
+    import regressors as R
+    Xs, U, Y = O.synthetic(n, d, p, seed=seed)
+    X = np.hstack((Xs, U)) if p else Xs
+    lsv = np.full(d, float(ls))
+    if Z is None:
+        np.random.seed(seed)
+        Z = O.draw_landmarks(Y, m)
+    holder = R.ThreeDimensionalKernel(ls, ls, ls, d) if kind == O.RBF else R.KernelWrapper(list(lsv))
+    reg = R.KoopmanNystromRegressor(p, kernel=holder, gamma=gamma, m=m)
+    reg.nystrom_centers_output = np.ascontiguousarray(Z.T)
+    reg.fit(X, Y)
+    want = O.fit(X, Y, p, kind, lsv, gamma, Z=Z)
+    return reg, want, (X, Y, Z, lsv)
+
+
+@pytest.mark.parametrize("n,d,p,m,kind", [
+    (3, 1, 0, 1, O.RBF),            # one landmark, one state, no controls, three samples
+    (2, 2, 1, 2, O.MATERN52),       # every sample is a landmark
+    (5, 192, 6, 3, O.RBF),          # cloth-shaped rows, far fewer samples than one 128-sample strip
+    (127, 3, 2, 7, O.MATERN52), (128, 3, 2, 7, O.RBF), (129, 3, 2, 7, O.RBF),        # strip edges
+    (511, 4, 1, 9, O.RBF), (512, 4, 1, 9, O.MATERN52), (513, 4, 1, 9, O.RBF), (1025, 4, 1, 9, O.RBF),   # chunk edges
+])
+def test_degenerate_and_edge_sizes(engine, n, d, p, m, kind):
+    reg, want, _ = _fit_pair(n, d, p, m, kind, 2.0, 1e-2)
+    assert reg.A.shape == (m, m) and reg.B.shape == (m, p) and reg.C.shape == (d, m) and reg.weights.shape == (d, m + p)
+    for k, got in (("A", reg.A), ("B", reg.B), ("C", reg.C), ("W", reg.weights)):
+        if got.size:
+            assert O.relerr(got, want[k]) <= 1e-9, (k, O.relerr(got, want[k]))
+
+
+def test_coincident_landmarks_are_carried_by_the_jitter(engine):
+    """Two identical landmark columns: K_zz is singular, K_mm = K_zz + 1e-6 I is not (regressors.py:139); S, S^-1 and the lift
+    still match the reference construction (eigenvalue 1e-6 => the comparison is held to 1e-6 relative)."""
+    n, d, p, m = 600, 3, 1, 12
+    Xs, U, Y = O.synthetic(n, d, p, seed=3)
+    np.random.seed(3)
+    Z = O.draw_landmarks(Y, m)
+    Z[5] = Z[2]
+    reg, want, (X, Y, Z, lsv) = _fit_pair(n, d, p, m, O.RBF, 1.5, 1e-3, seed=3, Z=Z)
+    phi = reg.lift(Xs[:9].T)
+    assert np.isfinite(phi).all() and O.relerr(phi, O.lift(Z, Xs[:9].T, O.RBF, lsv)) <= 1e-6
+    # the one-step predictor W [phi(x); u] is well defined even though the lifted coordinates are not: compare predictions
+    Xq = X[:50]
+    assert O.relerr(reg.predict(Xq), (want["W"] @ np.vstack((O.lift(Z, Xq[:, :d].T, O.RBF, lsv), Xq[:, d:].T))).T) <= 1e-6
+
+
+def test_samples_equal_to_landmarks_have_unit_kernel(engine):
+    """x == z gives r = 0 inside the fused lift (norm expansion): the kernel value must be 1 to rounding, for both kernels."""
+    import torch
+    d, m = 5, 40
+    rng = np.random.default_rng(0)
+    Z = rng.standard_normal((m, d)) * 3.0 + 7.0           # off-centre landmarks: the expansion cancels large norms
+    for kind, tol in ((O.RBF, 1e-12), (O.MATERN52, 1e-12)):   # Matern-5/2 is 1 - 5 r^2 / 6 + O(r^3): no linear term in r
+        X = np.hstack((Z, np.zeros((m, 1))))
+        Zd = torch.from_numpy(Z).cuda()
+        il = torch.full((d,), 1.0 / 2.0, dtype=torch.float64).cuda()
+        G = engine.grams(torch.from_numpy(X).cuda(), Zd, Zd, il, kind, 1)
+        K = O.kernel_matrix(Z, Z, kind, np.full(d, 2.0))
+        assert O.relerr(G["Gxx"].cpu().numpy(), K @ K.T) <= tol
+        Kzz = engine.kzz(Zd, il, kind).cpu().numpy()
+        assert np.array_equal(np.diag(Kzz), np.ones(m))   # direct-difference form: the diagonal is exactly 1
+
+
+def test_empty_block_inside_a_streamed_accumulation(engine):
+    import torch
+    n, d, p, m = 700, 6, 2, 20
+    Xs, U, Y = O.synthetic(n, d, p, seed=5)
+    X = torch.from_numpy(np.hstack((Xs, U))).cuda()
+    Yd = torch.from_numpy(Y).cuda()
+    np.random.seed(5)
+    Zd = torch.from_numpy(O.draw_landmarks(Y, m)).cuda()
+    il = torch.full((d,), 0.5, dtype=torch.float64).cuda()
+    whole = engine.grams(X, Yd, Zd, il, O.RBF, p)["_flat"].clone()
+    engine.gram_begin(Zd, il, O.RBF, p)
+    engine.gram_update(X[:300], Yd[:300])
+    engine.gram_update(X[300:300], Yd[300:300])          # empty block: a no-op
+    engine.gram_update(X[300:], Yd[300:])
+    parts = engine.gram_finalize()["_flat"]
+    assert O.relerr(parts.cpu().numpy(), whole.cpu().numpy()) <= 1e-13

@@ -76,6 +76,15 @@ def test_fit_argument_checks_do_not_need_gpu():
         reg2.fit(np.zeros((10, 3)), np.zeros((10, 2)))
 
 
+def test_more_landmarks_than_samples_raises_like_the_reference():
+    """regressors.py:130 draws without replacement: m > n is numpy's own ValueError, raised before any device work."""
+    import regressors as R
+    reg = R.KoopmanNystromRegressor(1, kernel=R.KernelWrapper([1, 1]), gamma=1e-6, m=50)
+    with pytest.raises(ValueError, match="larger sample than population"):
+        reg.fit(np.zeros((10, 3)), np.zeros((10, 2)))
+    assert reg.nystrom_centers_output is None
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():
