@@ -19,9 +19,12 @@ unpinned by its requirements.txt -- "parity unpinned" for these):
     these in the reference's order; ``solver='chol'`` is the SPD-Cholesky statement the GPU implements.
   * ``control.dlqr`` -> ``scipy.linalg.solve_discrete_are`` + K=(B'PB+R)^-1 B'PA (golden G4 pins it).
 
-Pinning: tests/test_oracle_vs_reference.py checks this file against the reference imported from
-/root/reference (when mounted) and tests/test_golden.py against fixtures the reference generated
-(tests/golden/make_golden.py) and against the reference's own result files G1..G4.
+Pinning: PINNED.  tests/test_oracle_vs_reference.py checks this file against the reference imported from
+/root/reference (when mounted); tests/test_oracle_golden.py and tests/test_oracle_cv_golden.py against fixtures the
+reference (and sklearn's GridSearchCV driving it) generated (tests/golden/make_golden*.py); tests/test_golden_g1.py,
+test_golden_g2.py and test_golden_g3.py against the reference's OWN published artefacts: the Duffing
+and cloth forecast-RMSE result files (G1, G2: 6 significant digits), a regressor pickled by the reference and its exported
+LQR gain (G3, G4).  Only the third-party library versions are unpinned (see above).
 """
 from __future__ import annotations
 
