@@ -327,7 +327,7 @@ def main():
     ap.add_argument("--d", type=int, default=192)
     ap.add_argument("--p", type=int, default=6)
     ap.add_argument("--gamma", type=float, default=1e-4)
-    ap.add_argument("--cpu-sample", type=int, default=16384)   # ~10-15 s of host work per sample pass
+    ap.add_argument("--cpu-sample", type=int, default=8192)   # ~7-20 s of host work per pass (single-threaded cdist dominates)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
