@@ -84,9 +84,9 @@ int nk_create(nk_handle **out, int device) {
 int nk_destroy(nk_handle *h) {
     if (!h) return NK_OK;
     cudaSetDevice(h->device);
-    nk_devbuf *bufs[] = {&h->zp, &h->inv_ls, &h->center, &h->xp[0], &h->xp[1], &h->yp[0], &h->yp[1], &h->psi[0], &h->psi[1],
-                         &h->gws, &h->items, &h->counters, &h->tile_of, &h->dinfo};
+    nk_devbuf *bufs[] = {&h->zp, &h->inv_ls, &h->center, &h->gws, &h->items, &h->counters, &h->tile_of, &h->dinfo};
     for (nk_devbuf *b : bufs) if (b->ptr) cudaFree(b->ptr);
+    for (int s = 0; s < kMaxSlots; s++) for (nk_devbuf *b : {&h->xp[s], &h->yp[s], &h->psi[s]}) if (b->ptr) cudaFree(b->ptr);
     for (nk_devbuf &b : h->dense) if (b.ptr) cudaFree(b.ptr);
     delete h;
     return NK_OK;
@@ -97,9 +97,10 @@ int nk_release_scratch(nk_handle *h) {
     h->gram_open = false;      // an accumulation in progress is discarded: nk_gram_update / _finalize need a new nk_gram_begin
     NK_CUDA(h, cudaSetDevice(h->device));
     NK_CUDA(h, cudaDeviceSynchronize());
-    nk_devbuf *bufs[] = {&h->zp, &h->inv_ls, &h->center, &h->xp[0], &h->xp[1], &h->yp[0], &h->yp[1], &h->psi[0], &h->psi[1],
-                         &h->gws, &h->items, &h->counters, &h->tile_of, &h->dinfo};
+    nk_devbuf *bufs[] = {&h->zp, &h->inv_ls, &h->center, &h->gws, &h->items, &h->counters, &h->tile_of, &h->dinfo};
     for (nk_devbuf *b : bufs) if (b->ptr) { cudaFree(b->ptr); b->ptr = nullptr; b->bytes = 0; }
+    for (int s = 0; s < kMaxSlots; s++)
+        for (nk_devbuf *b : {&h->xp[s], &h->yp[s], &h->psi[s]}) if (b->ptr) { cudaFree(b->ptr); b->ptr = nullptr; b->bytes = 0; }
     for (nk_devbuf &b : h->dense) if (b.ptr) { cudaFree(b.ptr); b.ptr = nullptr; b.bytes = 0; }
     return NK_OK;
 }
@@ -186,12 +187,20 @@ int nk_gram_begin(nk_handle *h, const double *Z, long long ldz, int m, int d, in
             for (int lb = 0; lb < MB; lb++) period.push_back(GramItem{kItemLift, side, lb, sb});
     for (int i = q2; i < h->n_sy; i++) period.push_back(sy[i]);
     h->period_len = (int)period.size();
+    // Chunks in flight.  With many landmarks one chunk's items (thousands of Gram tiles) fill the GPU and two buffers suffice;
+    // with few (the script configurations: m = 10 ... 400 gives 18 ... 150 items per chunk) the persistent CTAs would idle
+    // behind the pack -> lift -> Gram chain of a single chunk, so several chunks are kept in flight (one buffer set each).
+    h->nslots = 2;
+    if (h->period_len < 2 * h->sm_count) {
+        h->nslots = (3 * h->sm_count + h->period_len - 1) / h->period_len;
+        h->nslots = std::min(std::max(h->nslots, 2), kMaxSlots);
+    }
 
     int rc;
     if ((rc = ensure(h, h->zp, (size_t)h->MP * h->KLS * kSlabK * 8)) != NK_OK) return rc;
     if ((rc = ensure(h, h->inv_ls, (size_t)d * 8)) != NK_OK) return rc;
     if ((rc = ensure(h, h->center, (size_t)d * 8)) != NK_OK) return rc;
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < h->nslots; s++) {
         if ((rc = ensure(h, h->xp[s], (size_t)chunk * h->KLS * kSlabK * 8)) != NK_OK) return rc;
         if ((rc = ensure(h, h->yp[s], (size_t)chunk * h->KLS * kSlabK * 8)) != NK_OK) return rc;
         if ((rc = ensure(h, h->psi[s], (size_t)h->psi_rows * chunk * 8)) != NK_OK) return rc;
@@ -224,7 +233,8 @@ int nk_gram_update(nk_handle *h, const double *X, long long ldx, const double *Y
     if (!X || !Y || n < 0 || ldx < h->d + h->p || ldy < h->d) return set_err(h, NK_E_INVALID, "nk_gram_update: bad argument");
     NK_CUDA(h, cudaSetDevice(h->device));
     const long long n_chunks = (n + h->nk_chunk - 1) / h->nk_chunk;
-    if ((n_chunks + 1) * (long long)h->period_len > 2000000000LL || (n_chunks / 2 + 1) * (long long)h->n_sy * kConsumerWarps > 2000000000LL)
+    if ((n_chunks + 1) * (long long)h->period_len > 2000000000LL || (n_chunks / h->nslots + 1) * (long long)h->n_sy * kConsumerWarps > 2000000000LL
+        || n_chunks * (long long)kConsumerWarps > 2000000000LL)
         return set_err(h, NK_E_INVALID, "nk_gram_update: too many chunks for one call; split the sample block");
     GramParams P;
     P.X = X; P.ldx = ldx; P.Y = Y; P.ldy = ldy; P.n = n;
@@ -232,7 +242,12 @@ int nk_gram_update(nk_handle *h, const double *X, long long ldx, const double *Y
     P.MP = h->MP; P.KLS = h->KLS; P.nk = h->nk_chunk; P.n_chunks = (int)n_chunks;
     P.psi_rp = h->psi_rows / kPanel; P.e_row0 = 2 * h->MP; P.EP = h->EP;
     P.ZP = (const double *)h->zp.ptr; P.inv_ls = (const double *)h->inv_ls.ptr; P.center = (const double *)h->center.ptr;
-    for (int s = 0; s < 2; s++) { P.XP[s] = (double *)h->xp[s].ptr; P.YP[s] = (double *)h->yp[s].ptr; P.PSI[s] = (double *)h->psi[s].ptr; }
+    P.nslots = h->nslots;
+    P.eager_signal = h->nslots > 2;
+    for (int s = 0; s < kMaxSlots; s++) {
+        const int u = s < h->nslots ? s : 0;
+        P.XP[s] = (double *)h->xp[u].ptr; P.YP[s] = (double *)h->yp[u].ptr; P.PSI[s] = (double *)h->psi[u].ptr;
+    }
     P.Gws = (double *)h->gws.ptr;
     P.items = (const GramItem *)h->items.ptr;
     P.period_len = h->period_len; P.n_pk = h->n_pk; P.n_lf = h->n_lf; P.n_sy = h->n_sy;

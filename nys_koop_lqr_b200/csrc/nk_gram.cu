@@ -15,7 +15,10 @@
 //              fragment-ordered accumulator workspace with cp.reduce.async.bulk ... add.f64 (UBLKRED).
 //
 // The n x m feature matrix never exists: only a double-buffered chunk of nk samples (2 x 34.6 MB at m=4096,
-// nk=512) lives in the 126 MB L2.  Work items are claimed in a fixed global order from one atomic counter;
+// nk=512) lives in the 126 MB L2.  (With few landmarks -- the script configurations, m = 10 ... 400 -- one chunk's
+// items cannot fill 148 SMs, so up to 16 chunks are kept in flight, chunk c in buffer slot c % S, and a Gram item
+// signals its completion at once instead of after its next main loop: a Duffing fit, n = 69 900, m = 20, went from
+// 8.0 to 1.6 ms.)  Work items are claimed in a fixed global order from one atomic counter;
 // items of chunk c+1's pack/lift are spliced into the middle of chunk c's syrk items, and every cross-CTA
 // dependence (pack->lift->syrk->buffer reuse, and chunk order per accumulator tile) is a monotone counter in
 // global memory, so there is no grid-wide barrier and the summation order is fixed (deterministic results).
@@ -31,7 +34,7 @@
 
 namespace nk {
 
-struct __align__(16) QueuedItem { int type, chunk, a, b, c, pad0, pad1, pad2; };
+struct __align__(16) QueuedItem { int type, chunk, a, b, c, slot, pad1, pad2; };   // slot = chunk % nslots (set by the producer)
 
 struct GramSmemCtl {
     uint64_t full[kGramStages];
@@ -48,8 +51,7 @@ __device__ __forceinline__ void spin_until_ge(const int *ctr, int target) {
 // ------------------------------------------------------------------------------------------------
 // pack item: 128 samples -> XP, YP (lift operands) and the [U;Y] rows of Psi
 // ------------------------------------------------------------------------------------------------
-__device__ void do_pack(const GramParams &P, int chunk, int sb, int tid) {
-    const int slot = chunk & 1;
+__device__ void do_pack(const GramParams &P, int chunk, int slot, int sb, int tid) {
     const int warp = tid >> 5, lane = tid & 31;
     const long long s_base = (long long)chunk * P.nk + sb * kTile;
     const int KL = P.KLS * kSlabK;
@@ -146,20 +148,22 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                 }
             };
             QueuedItem it, nxt;
-            it.pad0 = it.pad1 = it.pad2 = 0; it.chunk = it.a = it.b = it.c = 0;
+            it.slot = it.pad1 = it.pad2 = 0; it.chunk = it.a = it.b = it.c = 0;
             nxt = it;
             bool valid = claim(it);
             for (;;) {
                 if (valid) {
                     // ---- dependences (all on items claimed earlier in the global order) ----
-                    // Counters are split by chunk parity: completions of chunk c+2 can only start after everything
-                    // of chunk c has finished (pack(c+2) waits for syrk(c)), so a per-parity count reaching its
-                    // target means exactly "all items of chunks c, c-2, ... are done".  One running total would let
-                    // early finishers of a later chunk stand in for a straggler of this one on small problems.
-                    const int par = it.chunk & 1, gen = it.chunk >> 1;
+                    // Counters are split by buffer slot (chunk c lives in slot c % S, S = 2 for large problems):
+                    // completions of chunk c+S can only start after everything of chunk c has finished (pack(c+S) waits
+                    // for syrk(c)), so a per-slot count reaching its target means exactly "all items of chunks c, c-S, ...
+                    // are done".  One running total would let early finishers of a later chunk stand in for a straggler
+                    // of this one on small problems.
+                    const int par = it.chunk % P.nslots, gen = it.chunk / P.nslots;
+                    it.slot = par;
                     if (it.type == kItemPack) {
-                        // buffers of this parity were last read by lift(chunk-2) / syrk(chunk-2)
-                        if (it.chunk >= 2) spin_until_ge(&P.counters[kCtrSyrk + par], gen * syrk_warps_per_chunk);
+                        // buffers of this slot were last read by lift(chunk-S) / syrk(chunk-S)
+                        if (gen >= 1) spin_until_ge(&P.counters[kCtrSyrk + par], gen * syrk_warps_per_chunk);
                     } else if (it.type == kItemLift) {
                         spin_until_ge(&P.counters[kCtrPack + par], (gen + 1) * P.n_pk);
                     } else {
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                 // ---- feed operand slabs ----
                 if (it.type != kItemPack) {
                     const double *Abase, *Bbase; size_t a_stride, b_stride; int nslabs;
-                    const int slot = it.chunk & 1;
+                    const int slot = it.slot;
                     if (it.type == kItemLift) {
                         Abase = P.ZP + (size_t)it.b * 16 * 128; a_stride = (size_t)(P.MP / kPanel) * 128;
                         Bbase = (it.a ? P.YP[slot] : P.XP[slot]) + (size_t)it.c * 16 * 128; b_stride = (size_t)(P.nk / kPanel) * 128;
@@ -257,11 +261,11 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
             if (it.type == kItemPack) {
                 TM_START(t_pk);
                 flush_pending();
-                do_pack(P, it.chunk, it.a, tid);
+                do_pack(P, it.chunk, it.slot, it.a, tid);
                 fence_proxy_async();   // generic-proxy stores are read back through the async proxy (bulk copies)
                 __threadfence();
                 named_bar_sync(1, kConsumerWarps * 32);
-                if (tid == 0) atomicAdd(&P.counters[kCtrPack + (it.chunk & 1)], 1);
+                if (tid == 0) atomicAdd(&P.counters[kCtrPack + it.slot], 1);
                 TM_ADD(2, t_pk);
                 continue;
             }
@@ -334,8 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                 // indices), which with the double-precision exp / Matern bodies is ~240 KB of SASS that thrashes the
                 // instruction cache once per item (measured: the epilogue then costs as much as the item's main loop).
                 // Each lane reads back exactly what it wrote (no cross-lane traffic).
-                const int slot = it.chunk & 1;
-                double *psi = P.PSI[slot];
+                double *psi = P.PSI[it.slot];
                 const long long s_chunk = (long long)it.chunk * P.nk;
 #pragma unroll
                 for (int i = 0; i < 8; i++)
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                 fence_proxy_async();
                 __threadfence();
                 __syncwarp();
-                if (lane == 0) atomicAdd(&P.counters[kCtrLift + (it.chunk & 1)], 1);
+                if (lane == 0) atomicAdd(&P.counters[kCtrLift + it.slot], 1);
                 TM_ADD(7, t_ep);
             } else {
                 // Gram epilogue: accumulators -> this warp's 16 KB staging buffer -> one asynchronous bulk reduce-add
@@ -383,7 +386,8 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 pend_ver = ver;
-                pend_par = it.chunk & 1;
+                pend_par = it.slot;
+                if (P.eager_signal) flush_pending();   // small problems: the same tile of the next chunk (another CTA) is waiting for this
                 TM_ADD(8, t_ep);
             }
         }

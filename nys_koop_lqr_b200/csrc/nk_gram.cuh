@@ -5,6 +5,7 @@
 namespace nk {
 
 enum ItemType : int { kItemPack = 0, kItemLift = 1, kItemSyrk = 2 };
+constexpr int kMaxSlots = 16;
 
 // One entry of the per-chunk work period.  pack: a = sample sub-block;  lift: a = side (0: x_t, 1: x_{t+1}),
 // b = landmark block, c = sample sub-block;  syrk: a, b = 128-row blocks of the stacked feature matrix
@@ -26,19 +27,23 @@ struct GramParams {
     const double *ZP;       // packed, scaled, augmented landmarks: MP/8 panels x KLS slabs
     const double *inv_ls;   // (d) 1/length_scale
     const double *center;   // (d) shift applied to samples and landmarks before the norm expansion
-    double *XP[2], *YP[2];  // packed scaled sample operands of the lift, double-buffered per chunk parity
-    double *PSI[2];         // packed feature chunk, double-buffered: psi_rp panels x nk/16 slabs
+    int nslots;             // chunk buffers in flight: chunk c lives in slot c % nslots (2 for large m; more when one chunk's items
+                            // cannot fill the GPU, see nk_gram_begin)
+    int eager_signal;       // != 0: a Gram item signals its completion at once (small problems: the next chunk's tile is waiting for it)
+    double *XP[kMaxSlots], *YP[kMaxSlots];  // packed scaled sample operands of the lift, one buffer per slot
+    double *PSI[kMaxSlots];                 // packed feature chunk per slot: psi_rp panels x nk/16 slabs
     double *Gws;            // accumulator tiles in C-fragment order, 16384 doubles each
     const GramItem *items;  // one period: syrk(c) items with pack(c+1) and lift(c+1) items spliced in
     int period_len, n_pk, n_lf, n_sy;
 #ifdef NK_GRAM_TIMING
     long long *timing;      // development build only: 16 cycle counters per consumer warp (tools/gram_timing.py)
 #endif
-    int *counters;          // [0] next item; per chunk parity: [2+par] packs done, [4+par] lift warps done, [6+par] syrk warps done; [16+t] tile versions
+    int *counters;          // [0] next item; per slot s: [kCtrPack+s] packs done, [kCtrLift+s] lift warps done, [kCtrSyrk+s] syrk warps done;
+                            // [kCounterTileVer+t] tile versions
 };
 
-constexpr int kCtrPack = 2, kCtrLift = 4, kCtrSyrk = 6;
-constexpr int kCounterTileVer = 16;
+constexpr int kCtrPack = 16, kCtrLift = 32, kCtrSyrk = 48;
+constexpr int kCounterTileVer = 64;
 constexpr int kGramStages = 3;
 constexpr int kItemQueue = 4;
 constexpr size_t kGramStageBytes = (size_t)kGramStages * 2 * kSlabTileDoubles * 8;      // 96 KB operand ring

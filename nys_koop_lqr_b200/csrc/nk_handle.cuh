@@ -23,7 +23,8 @@ struct nk_handle {
     int MP = 0, KLS = 0, EP = 0, psi_rows = 0, nblk = 0, ntiles = 0;
     int n_pk = 0, n_lf = 0, n_sy = 0, period_len = 0;
     double last_flops = 0.0;
-    nk_devbuf zp, inv_ls, center, xp[2], yp[2], psi[2], gws, items, counters, tile_of;
+    nk_devbuf zp, inv_ls, center, xp[nk::kMaxSlots], yp[nk::kMaxSlots], psi[nk::kMaxSlots], gws, items, counters, tile_of;
+    int nslots = 2;
     std::vector<int> h_tile_of;
 
     // ---- dense-stage scratch (grow-only), see nk_dense.cu ----

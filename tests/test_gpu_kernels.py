@@ -63,6 +63,23 @@ def test_gram_parity(engine, n, d, p, m, kind, ls, chunk):
     assert torch.equal(G["Gxx"], G["Gxx"].T) and torch.equal(G["Gyy"], G["Gyy"].T)
 
 
+@pytest.mark.parametrize("n,d,p,m,chunk", [(20000, 2, 1, 20, 128), (20000, 6, 2, 300, 128), (30000, 3, 1, 600, 256), (9000, 4, 1, 1000, 128)])
+def test_gram_many_chunks_in_flight(engine, n, d, p, m, chunk):
+    """Few landmarks: one chunk's items cannot fill the GPU, so nk_gram_begin keeps several chunks in flight (chunk c in buffer
+    slot c % S, up to 16 slots; S = 2 again from m ~ 1000).  Every slot is reused many times here (n / chunk >> S): parity with
+    the oracle, and bit-identical reruns (per-tile chunk order is fixed by the tile's version counter whatever the slot count)."""
+    Xs, U, Y, Z = make_problem(n, d, p, m, seed=m)
+    lsv = np.full(d, 1.5)
+    ref = O.grams(Xs, Y, U, Z, O.MATERN52, lsv)
+    Xa, Yd, Zd, il = dev(np.hstack((Xs, U))), dev(Y), dev(Z), dev(1.0 / lsv)
+    G = engine.grams(Xa, Yd, Zd, il, O.MATERN52, p, chunk)
+    Gb = engine.grams(Xa, Yd, Zd, il, O.MATERN52, p, chunk)
+    torch.cuda.synchronize()
+    assert torch.equal(G["_flat"], Gb["_flat"]), "not run-to-run deterministic with several chunks in flight"
+    for k in ("Gxx", "Gyx", "Gyy", "Gxu", "Gyu", "Guu", "GYy"):
+        assert O.relerr(host(G[k]), ref[k]) <= 1e-12, k
+
+
 def test_gram_streaming_and_determinism(engine):
     """update() over sample blocks == one shot (shard-sum invariance, <=1e-13), and reruns are bit-identical."""
     n, d, p, m = 4000, 24, 2, 150
