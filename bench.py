@@ -31,6 +31,27 @@ METRIC = "Nystrom-Koopman fit samples/s (n=1e7, m=4096)"
 UNIT = "samples/s"
 
 
+# ----------------------------------------------------------------------------------------------------------
+# stdout carries exactly ONE line (the JSON result): everything else any library writes to file descriptor 1 (NCCL prints an
+# "NCCL version ..." line there when NCCL_DEBUG is VERSION or WARN, torchrun banners, ...) is sent to stderr instead
+# ----------------------------------------------------------------------------------------------------------
+_RESULT_OUT = None
+
+
+def protect_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def algorithmic_flops_per_sample(m, d, p):
     """lifts 4md, two symmetric Grams m^2 each, cross Gram 2m^2, 2x2mp control products, 2md reconstruction."""
     return 4.0 * m * m + 6.0 * m * d + 4.0 * m * p
@@ -137,7 +158,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -192,8 +213,7 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local_rank)
     distributed = world > 1
     if distributed:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # the image's default prints an "NCCL version" line on stdout next to the JSON line
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # its output (incl. the version banner) lands on stderr: see protect_stdout
         dist.init_process_group("nccl", device_id=dev)
     eng = Engine.get(local_rank)
     n, d, p, m = args.n, args.d, args.p, args.m
@@ -309,7 +329,7 @@ def run_gpu_arm(args):
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "model_check": {"A_shape": list(reg.A.shape), "A_fro": float(np.linalg.norm(reg.A)), "finite": bool(np.isfinite(reg.A).all() and np.isfinite(reg.C).all())},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
@@ -332,6 +352,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    protect_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))

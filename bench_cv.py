@@ -26,6 +26,27 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+# ----------------------------------------------------------------------------------------------------------
+# stdout carries exactly ONE line (the JSON result): everything else any library writes to file descriptor 1 (NCCL prints an
+# "NCCL version ..." line there when NCCL_DEBUG is VERSION or WARN, torchrun banners, ...) is sent to stderr instead
+# ----------------------------------------------------------------------------------------------------------
+_RESULT_OUT = None
+
+
+def protect_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--samples", "--n", dest="n", type=int, default=2_000_000)
@@ -38,6 +59,7 @@ def main():
     ap.add_argument("--traj", type=int, default=100_000)
     ap.add_argument("--T", type=int, default=101)
     args = ap.parse_args()
+    protect_stdout()
 
     import torch
     import regressors as R
@@ -52,8 +74,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # lands on stderr (protect_stdout)
         dist.init_process_group("nccl", device_id=dev)
     eng = Engine.get(local_rank)
     n_total, m, d, p = args.n, args.m, args.d, args.p
@@ -147,7 +168,7 @@ def main():
         "dtype": "f64", "data": "synthetic", "n_gpus": world,
     }
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
