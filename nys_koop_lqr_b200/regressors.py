@@ -133,6 +133,7 @@ class KoopmanNystromRegressor(KoopmanRegressor):
     """
 
     stream_block = 262144     # samples per host->device block when inputs live in host memory
+    device_block = 1 << 24    # samples per fused-kernel launch when inputs are already on the device
     gram_chunk = 0            # samples per on-chip feature chunk (0: library default 512)
 
     def __init__(self, n_inputs, kernel=None, gamma=None, m=None):
@@ -208,7 +209,8 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         on_device = isinstance(X, torch.Tensor) and X.is_cuda and isinstance(Y, torch.Tensor) and Y.is_cuda
         if on_device:
             Xd, Yd = _as_device_rows(eng, X), _as_device_rows(eng, Y)
-            eng.gram_update(Xd, Yd)
+            for s in range(0, n, self.device_block):       # one launch for n <= 2^24; nk_gram_update bounds the chunks per call
+                eng.gram_update(Xd[s:s + self.device_block], Yd[s:s + self.device_block])
             return
         blk = int(self.stream_block)
         if n <= blk:

@@ -114,3 +114,36 @@ def test_streaming_host_fit_equals_resident_fit(engine):
     c = make(); c.fit(X, Y)
     assert O.relerr(b.A, a.A) <= 1e-9 and O.relerr(b.C, a.C) <= 1e-9
     assert np.array_equal(c.A, a.A)
+
+
+def test_input_layouts_the_scripts_pass(engine):
+    """The scripts call fit(X.T, Y.T) with X (d+p, n) C-ordered, i.e. Fortran-ordered (n, d+p) views; CV folds are row slices of
+    such views; user code may hand float32.  All must give the model of the plain C-ordered float64 call -- also through the
+    streamed (blocked host upload) path."""
+    import regressors as R
+    Xs, U, Y = O.synthetic(5000, d=5, p=2, seed=11)
+    X = np.hstack((Xs, U))
+    np.random.seed(1)
+    Z = O.draw_landmarks(Y, 40).T.copy()
+    def make(block=None):
+        r = R.KoopmanNystromRegressor(2, kernel=R.KernelWrapper([2.0] * 5), gamma=1e-3, m=40)
+        r.nystrom_centers_output = Z
+        if block:
+            r.stream_block = block
+        return r
+    base = make(); base.fit(X, Y)
+    XT, YT = np.ascontiguousarray(X.T), np.ascontiguousarray(Y.T)          # (d+p, n), (d, n) as the scripts hold them
+    f = make(); f.fit(XT.T, YT.T)
+    assert np.array_equal(f.A, base.A) and np.array_equal(f.C, base.C)
+    g = make(block=777); g.fit(XT.T, YT.T)                                   # streamed, ragged blocks, strided host source
+    assert O.relerr(g.A, base.A) <= 1e-9 and O.relerr(g.B, base.B) <= 1e-9 and O.relerr(g.C, base.C) <= 1e-9
+    s1 = make(); s1.fit(XT.T[100:3100], YT.T[100:3100])                      # a fold: row slice of the strided view
+    s2 = make(); s2.fit(np.ascontiguousarray(X[100:3100]), np.ascontiguousarray(Y[100:3100]))
+    assert np.array_equal(s1.A, s2.A)
+    h = make(); h.fit(X.astype(np.float32), Y.astype(np.float32))             # float32 in: promoted, like numpy would
+    h64 = make(); h64.fit(X.astype(np.float32).astype(np.float64), Y.astype(np.float32).astype(np.float64))
+    assert np.array_equal(h.A, h64.A)
+    # lift / predict accept the same variety
+    q = np.asfortranarray(Xs[:9].T)
+    assert np.array_equal(base.lift(q), base.lift(np.ascontiguousarray(q)))
+    assert np.array_equal(base.predict(np.asfortranarray(X[:9])), base.predict(X[:9]))
