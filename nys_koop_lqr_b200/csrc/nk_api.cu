@@ -243,7 +243,6 @@ int nk_gram_update(nk_handle *h, const double *X, long long ldx, const double *Y
     P.psi_rp = h->psi_rows / kPanel; P.e_row0 = 2 * h->MP; P.EP = h->EP;
     P.ZP = (const double *)h->zp.ptr; P.inv_ls = (const double *)h->inv_ls.ptr; P.center = (const double *)h->center.ptr;
     P.nslots = h->nslots;
-    P.eager_signal = h->nslots > 2;
     for (int s = 0; s < kMaxSlots; s++) {
         const int u = s < h->nslots ? s : 0;
         P.XP[s] = (double *)h->xp[u].ptr; P.YP[s] = (double *)h->yp[u].ptr; P.PSI[s] = (double *)h->psi[u].ptr;

@@ -107,6 +107,10 @@ __device__ void do_pack(const GramParams &P, int chunk, int slot, int sb, int ti
 // ------------------------------------------------------------------------------------------------
 // the persistent kernel
 // ------------------------------------------------------------------------------------------------
+// kMulti = false: two chunk buffers (slot = chunk parity), deferred completion signal -- the large-m configuration, kept as
+// its own instantiation so that its instruction schedule does not depend on the small-problem generalisation (the merged
+// runtime-S version measured 0.7% slower at m=4096 on the same box).  kMulti = true: S = P.nslots buffers, immediate signal.
+template <bool kMulti>
 __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     double *stage_base = reinterpret_cast<double *>(smem_raw);
@@ -159,7 +163,8 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                     // for syrk(c)), so a per-slot count reaching its target means exactly "all items of chunks c, c-S, ...
                     // are done".  One running total would let early finishers of a later chunk stand in for a straggler
                     // of this one on small problems.
-                    const int par = it.chunk % P.nslots, gen = it.chunk / P.nslots;
+                    const int par = kMulti ? it.chunk % P.nslots : (it.chunk & 1);
+                    const int gen = kMulti ? it.chunk / P.nslots : (it.chunk >> 1);
                     it.slot = par;
                     if (it.type == kItemPack) {
                         // buffers of this slot were last read by lift(chunk-S) / syrk(chunk-S)
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                 // ---- feed operand slabs ----
                 if (it.type != kItemPack) {
                     const double *Abase, *Bbase; size_t a_stride, b_stride; int nslabs;
-                    const int slot = it.slot;
+                    const int slot = kMulti ? it.slot : (it.chunk & 1);
                     if (it.type == kItemLift) {
                         Abase = P.ZP + (size_t)it.b * 16 * 128; a_stride = (size_t)(P.MP / kPanel) * 128;
                         Bbase = (it.a ? P.YP[slot] : P.XP[slot]) + (size_t)it.c * 16 * 128; b_stride = (size_t)(P.nk / kPanel) * 128;
@@ -261,11 +266,11 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
             if (it.type == kItemPack) {
                 TM_START(t_pk);
                 flush_pending();
-                do_pack(P, it.chunk, it.slot, it.a, tid);
+                do_pack(P, it.chunk, kMulti ? it.slot : (it.chunk & 1), it.a, tid);
                 fence_proxy_async();   // generic-proxy stores are read back through the async proxy (bulk copies)
                 __threadfence();
                 named_bar_sync(1, kConsumerWarps * 32);
-                if (tid == 0) atomicAdd(&P.counters[kCtrPack + it.slot], 1);
+                if (tid == 0) atomicAdd(&P.counters[kCtrPack + (kMulti ? it.slot : (it.chunk & 1))], 1);
                 TM_ADD(2, t_pk);
                 continue;
             }
@@ -338,7 +343,8 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                 // indices), which with the double-precision exp / Matern bodies is ~240 KB of SASS that thrashes the
                 // instruction cache once per item (measured: the epilogue then costs as much as the item's main loop).
                 // Each lane reads back exactly what it wrote (no cross-lane traffic).
-                double *psi = P.PSI[it.slot];
+                const int slot = kMulti ? it.slot : (it.chunk & 1);
+                double *psi = P.PSI[slot];
                 const long long s_chunk = (long long)it.chunk * P.nk;
 #pragma unroll
                 for (int i = 0; i < 8; i++)
@@ -364,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                 fence_proxy_async();
                 __threadfence();
                 __syncwarp();
-                if (lane == 0) atomicAdd(&P.counters[kCtrLift + it.slot], 1);
+                if (lane == 0) atomicAdd(&P.counters[kCtrLift + slot], 1);
                 TM_ADD(7, t_ep);
             } else {
                 // Gram epilogue: accumulators -> this warp's 16 KB staging buffer -> one asynchronous bulk reduce-add
@@ -386,8 +392,8 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 pend_ver = ver;
-                pend_par = it.slot;
-                if (P.eager_signal) flush_pending();   // small problems: the same tile of the next chunk (another CTA) is waiting for this
+                pend_par = kMulti ? it.slot : (it.chunk & 1);
+                if (kMulti) flush_pending();   // small problems: the same tile of the next chunk (another CTA) is waiting for this
                 TM_ADD(8, t_ep);
             }
         }
@@ -405,12 +411,15 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
 void launch_gram(const GramParams &P, int sm_count, cudaStream_t stream, cudaError_t *err) {
     static unsigned long long configured = 0;
     if (first_use_on_device(configured)) {
-        *err = cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGramSmemBytes);
+        *err = cudaFuncSetAttribute(gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGramSmemBytes);
+        if (*err != cudaSuccess) return;
+        *err = cudaFuncSetAttribute(gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGramSmemBytes);
         if (*err != cudaSuccess) return;
     }
+    const void *kernel = P.nslots > 2 ? (const void *)gram_kernel<true> : (const void *)gram_kernel<false>;
     // every CTA must be resident (items wait on items claimed earlier): cooperative launch guarantees it
     int max_blocks = 0;
-    *err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, gram_kernel, kThreads, kGramSmemBytes);
+    *err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, gram_kernel<false>, kThreads, kGramSmemBytes);
     if (*err != cudaSuccess) return;
     if (max_blocks < 1) { *err = cudaErrorLaunchOutOfResources; return; }
     long long total_items = (long long)(P.n_chunks + 1) * P.period_len;
@@ -418,7 +427,7 @@ void launch_gram(const GramParams &P, int sm_count, cudaStream_t stream, cudaErr
     if (total_items < grid) grid = (int)total_items;
     if (grid < 1) grid = 1;
     void *args[] = {(void *)&P};
-    *err = cudaLaunchCooperativeKernel((void *)gram_kernel, dim3(grid), dim3(kThreads), args, kGramSmemBytes, stream);
+    *err = cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kThreads), args, kGramSmemBytes, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

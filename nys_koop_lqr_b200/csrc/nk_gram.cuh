@@ -29,7 +29,6 @@ struct GramParams {
     const double *center;   // (d) shift applied to samples and landmarks before the norm expansion
     int nslots;             // chunk buffers in flight: chunk c lives in slot c % nslots (2 for large m; more when one chunk's items
                             // cannot fill the GPU, see nk_gram_begin)
-    int eager_signal;       // != 0: a Gram item signals its completion at once (small problems: the next chunk's tile is waiting for it)
     double *XP[kMaxSlots], *YP[kMaxSlots];  // packed scaled sample operands of the lift, one buffer per slot
     double *PSI[kMaxSlots];                 // packed feature chunk per slot: psi_rp panels x nk/16 slabs
     double *Gws;            // accumulator tiles in C-fragment order, 16384 doubles each
