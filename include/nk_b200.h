@@ -87,7 +87,9 @@ int nk_sym_sqrt(nk_handle *h, int n, const double *K, long long ldk, double lamb
 /* ---- Grams -> Koopman matrices  (regressors.py:147-169) ----
  * inner = [[Gxx + gn*Kmm, Gxu],[Gxu^T, Guu + gn*I]],  G = S^-1 [Gyx|Gyu] inner^-1 blkdiag(Kzz S^-1, I_p)
  * A = G[:, :m], B = G[:, m:];  C = GYy (gn*Kmm + Gyy)^-1 S;  W = C G;  Kmm = Kzz + jitter*I.
- * Outputs: A (m,m), B (m,p), C (d,m), W (d,m+p).  info (host): 0, or 1/2 if the first/second system is not SPD. */
+ * Outputs: A (m,m), B (m,p), C (d,m), W (d,m+p).  info (host): 0, or 1/2 if the first/second system is not SPD.
+ * The call synchronises the stream twice to read the two Cholesky verdicts; when it returns NK_OK, A and B are COMPLETE on
+ * the device (a caller may start downloading them on another stream), C and W complete in stream order. */
 int nk_solve_abc(nk_handle *h, int m, int p, int d, double gamma_n, double jitter,
                  const double *Gxx, const double *Gyx, const double *Gyy, const double *Gxu, const double *Gyu,
                  const double *Guu, const double *GYy, const double *Kzz, const double *S, const double *Sinv,

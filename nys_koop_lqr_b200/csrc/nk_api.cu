@@ -72,8 +72,10 @@ int nk_create(nk_handle **out, int device) {
     e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) return set_err(nullptr, NK_E_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
     if (prop.major != 10) return set_err(nullptr, NK_E_CUDA, "nk_create: device is not sm_100 (kernels are built for sm_100a only)");
-    e = cudaSetDevice(device);
-    if (e != cudaSuccess) return set_err(nullptr, NK_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    {
+        DeviceScope scope(device);      // makes sure the device can be selected; the caller's current device is left alone
+        if (scope.err != cudaSuccess) return set_err(nullptr, NK_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(scope.err));
+    }
     nk_handle *h = new nk_handle();
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
@@ -83,7 +85,7 @@ int nk_create(nk_handle **out, int device) {
 
 int nk_destroy(nk_handle *h) {
     if (!h) return NK_OK;
-    cudaSetDevice(h->device);
+    DeviceScope scope(h->device);
     nk_devbuf *bufs[] = {&h->zp, &h->inv_ls, &h->center, &h->gws, &h->items, &h->counters, &h->tile_of, &h->dinfo};
     for (nk_devbuf *b : bufs) if (b->ptr) cudaFree(b->ptr);
     for (int s = 0; s < kMaxSlots; s++) for (nk_devbuf *b : {&h->xp[s], &h->yp[s], &h->psi[s]}) if (b->ptr) cudaFree(b->ptr);
@@ -95,7 +97,7 @@ int nk_destroy(nk_handle *h) {
 int nk_release_scratch(nk_handle *h) {
     if (!h) return NK_E_INVALID;
     h->gram_open = false;      // an accumulation in progress is discarded: nk_gram_update / _finalize need a new nk_gram_begin
-    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_ON_DEVICE(h);
     NK_CUDA(h, cudaDeviceSynchronize());
     nk_devbuf *bufs[] = {&h->zp, &h->inv_ls, &h->center, &h->gws, &h->items, &h->counters, &h->tile_of, &h->dinfo};
     for (nk_devbuf *b : bufs) if (b->ptr) { cudaFree(b->ptr); b->ptr = nullptr; b->bytes = 0; }
@@ -112,7 +114,7 @@ long long nk_launch_count(nk_handle *h) { return h ? h->launches : 0; }
 
 int nk_probe_dmma_tflops(nk_handle *h, double ms_target, double *tflops) {
     if (!h || !tflops) return NK_E_INVALID;
-    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_ON_DEVICE(h);
     int rc;
     const int ctas = h->sm_count * 2;
     if ((rc = ensure(h, h->dense[11], (size_t)ctas * 256 * 8)) != NK_OK) return rc;
@@ -142,7 +144,7 @@ int nk_gram_begin(nk_handle *h, const double *Z, long long ldz, int m, int d, in
     if (!Z || !inv_ls || m < 1 || d < 1 || p < 0 || ldz < d) return set_err(h, NK_E_INVALID, "nk_gram_begin: bad argument");
     if (kind != NK_KERNEL_RBF && kind != NK_KERNEL_MATERN52) return set_err(h, NK_E_INVALID, "nk_gram_begin: unsupported kernel kind");
     if (p > kTile) return set_err(h, NK_E_INVALID, "nk_gram_begin: more than 128 control inputs are not supported");
-    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_ON_DEVICE(h);
     if (chunk <= 0) chunk = 512;
     chunk = ((chunk + kTile - 1) / kTile) * kTile;
     h->m = m; h->d = d; h->p = p; h->kind = kind; h->nk_chunk = chunk;
@@ -231,7 +233,7 @@ int nk_gram_update(nk_handle *h, const double *X, long long ldx, const double *Y
     if (!h->gram_open) return set_err(h, NK_E_STATE, "nk_gram_update: call nk_gram_begin first");
     if (n == 0) return NK_OK;
     if (!X || !Y || n < 0 || ldx < h->d + h->p || ldy < h->d) return set_err(h, NK_E_INVALID, "nk_gram_update: bad argument");
-    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_ON_DEVICE(h);
     const long long n_chunks = (n + h->nk_chunk - 1) / h->nk_chunk;
     if ((n_chunks + 1) * (long long)h->period_len > 2000000000LL || (n_chunks / h->nslots + 1) * (long long)h->n_sy * kConsumerWarps > 2000000000LL
         || n_chunks * (long long)kConsumerWarps > 2000000000LL)
@@ -283,7 +285,7 @@ int nk_gram_finalize(nk_handle *h, double *Gxx, long long ld_gxx, double *Gyx, l
     if (!h) return NK_E_INVALID;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!h->gram_open) return set_err(h, NK_E_STATE, "nk_gram_finalize: call nk_gram_begin first");
-    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_ON_DEVICE(h);
     const double *G = (const double *)h->gws.ptr;
     const int *tof = (const int *)h->tile_of.ptr;
     const int m = h->m, p = h->p, d = h->d, MP = h->MP, E0 = 2 * h->MP, nb = h->nblk;

@@ -99,7 +99,7 @@ int nk_kernel_function(nk_handle *h, int kind, long long count, const double *ex
     if (!h) return NK_E_INVALID;
     if (count < 0 || !exponent || !out || (kind != NK_KERNEL_RBF && kind != NK_KERNEL_MATERN52)) return set_err(h, NK_E_INVALID, "nk_kernel_function: bad argument");
     if (count == 0) return NK_OK;
-    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_ON_DEVICE(h);
     const long long blocks = (count + 255) / 256;
     kernel_function_kernel<<<(unsigned)(blocks < 8192 ? blocks : 8192), 256, 0, (cudaStream_t)stream_>>>(count, kind, exponent, out);
     h->launches++;
@@ -111,7 +111,7 @@ int nk_axpy(nk_handle *h, long long count, double alpha, const double *x, double
     if (!h) return NK_E_INVALID;
     if (count < 0 || !x || !y) return set_err(h, NK_E_INVALID, "nk_axpy: bad argument");
     if (count == 0) return NK_OK;
-    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_ON_DEVICE(h);
     const long long blocks = (count + 255) / 256;
     axpy_kernel<<<(unsigned)(blocks < 8192 ? blocks : 8192), 256, 0, (cudaStream_t)stream_>>>(count, alpha, x, y);
     h->launches++;
@@ -126,7 +126,7 @@ int nk_cv_weights(nk_handle *h, int m, int p, int d, int nlam, const double *gam
     cudaStream_t stream = (cudaStream_t)stream_;
     if (m < 1 || p < 0 || d < 1 || nlam < 1 || nlam > 4096 || !gamma_n || !Gxx || !Gyx || !Gyy || !GYy || !Kzz || !Wk || (p && (!Gxu || !Gyu || !Guu)))
         return set_err(h, NK_E_INVALID, "nk_cv_weights: bad argument");
-    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_ON_DEVICE(h);
     int rc;
     const int N1 = m + p, ld1 = even_c(N1), ldm = even_c(m);
     const int nblk1 = (N1 + kDBc - 1) / kDBc, nblkm = (m + kDBc - 1) / kDBc;
@@ -206,7 +206,7 @@ int nk_cv_score(nk_handle *h, const double *Z, long long ldz, int m, int d, int 
         return set_err(h, NK_E_INVALID, "nk_cv_score: bad argument");
     if (kind != NK_KERNEL_RBF && kind != NK_KERNEL_MATERN52) return set_err(h, NK_E_INVALID, "nk_cv_score: unsupported kernel kind");
     if (N == 0) return NK_OK;
-    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_ON_DEVICE(h);
     // Predictions of all stacked weight rows at once on the packed persistent GEMM (nk_pgemm.cu): the held-out block's kernel
     // rows are written straight into the packed operand layout by the kernel-lift GEMM epilogue, the controls are dropped
     // into the p spare contraction columns, the stacked weights are packed once per call.

@@ -629,7 +629,7 @@ int nk_gemm(nk_handle *h, int transa, int transb, int M, int N, int K, double al
     if (!h) return NK_E_INVALID;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (M < 0 || N < 0 || K < 0 || !A || !B || !C) return set_err(h, NK_E_INVALID, "nk_gemm: bad argument");
-    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_ON_DEVICE(h);
     int rc = NK_OK;
     const double *Ak = A; long long ldak = lda;      // (M,K) k-contiguous
     const double *Bk = B; long long ldbk = ldb;      // (N,K) k-contiguous
@@ -650,7 +650,7 @@ int nk_potrf(nk_handle *h, int n, double *A, long long lda, int *info, void *str
     if (!h) return NK_E_INVALID;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n < 1 || !A || lda < n) return set_err(h, NK_E_INVALID, "nk_potrf: bad argument");
-    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_ON_DEVICE(h);
     int rc;
     const int nblk = (n + kDB - 1) / kDB;
     double *dinv = dense_scratch(h, 8, (size_t)nblk * kDB * kDB, &rc); if (rc) return rc;
@@ -669,7 +669,7 @@ int nk_trsm_lower(nk_handle *h, int trans, int n, int nrhs, const double *L, lon
     if (!h) return NK_E_INVALID;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n < 1 || nrhs < 1 || !L || !B) return set_err(h, NK_E_INVALID, "nk_trsm_lower: bad argument");
-    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_ON_DEVICE(h);
     // generic entry: rebuilds the diagonal-block inverses from L (the fused paths reuse the ones potrf produced)
     int rc;
     const int nblk = (n + kDB - 1) / kDB, ldn = even(n);
@@ -702,7 +702,7 @@ int nk_sym_sqrt(nk_handle *h, int n, const double *K, long long ldk, double lamb
     if (!h) return NK_E_INVALID;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n < 1 || !K || !S || !Sinv || !(lambda_min_bound > 0.0)) return set_err(h, NK_E_INVALID, "nk_sym_sqrt: bad argument");
-    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_ON_DEVICE(h);
     int rc;
     const int ldn = even(n), nblk = (n + kDB - 1) / kDB;
     const size_t nn = (size_t)n * ldn;
@@ -790,7 +790,7 @@ int nk_solve_abc(nk_handle *h, int m, int p, int d, double gamma_n, double jitte
     cudaStream_t stream = (cudaStream_t)stream_;
     if (m < 1 || p < 0 || d < 1 || !Gxx || !Gyx || !Gyy || !GYy || !Kzz || !S || !Sinv || !A || !C || !W || (p && (!Gxu || !Gyu || !Guu || !B)))
         return set_err(h, NK_E_INVALID, "nk_solve_abc: bad argument");
-    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_ON_DEVICE(h);
     if (info) *info = 0;
     int rc;
     const int N1 = m + p, ld1 = even(N1), ldm = even(m), nblk1 = (N1 + kDB - 1) / kDB;
@@ -854,7 +854,7 @@ int nk_kernel_cross(nk_handle *h, const double *Z, long long ldz, int m, int d, 
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!Z || !X || !K || !inv_ls || m < 1 || d < 1 || N < 1 || N > 2000000000LL) return set_err(h, NK_E_INVALID, "nk_kernel_cross: bad argument");
     if (kind != NK_KERNEL_RBF && kind != NK_KERNEL_MATERN52) return set_err(h, NK_E_INVALID, "nk_kernel_cross: unsupported kernel kind");
-    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_ON_DEVICE(h);
     int rc;
     const int KA = even(d + 2);
     double *Za = dense_scratch(h, 0, (size_t)m * KA, &rc); if (rc) return rc;

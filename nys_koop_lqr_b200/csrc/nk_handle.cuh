@@ -38,6 +38,27 @@ int check_cuda(nk_handle *h, cudaError_t e, const char *what);
 int ensure(nk_handle *h, nk_devbuf &b, size_t bytes);
 }  // namespace nk
 
+namespace nk {
+// Every entry point runs on the handle's device and leaves the CALLER's current device as it found it (a process may drive
+// several GPUs; changing the current device behind the caller's back makes its next allocation land on the wrong GPU).
+struct DeviceScope {
+    int prev = -1;
+    bool changed = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceScope(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) { err = cudaSetDevice(dev); changed = (err == cudaSuccess); }
+    }
+    ~DeviceScope() { if (changed) cudaSetDevice(prev); }
+    DeviceScope(const DeviceScope &) = delete;
+    DeviceScope &operator=(const DeviceScope &) = delete;
+};
+}  // namespace nk
+
+#define NK_ON_DEVICE(h)                                                      \
+    nk::DeviceScope _nk_device_scope((h)->device);                           \
+    NK_CUDA((h), _nk_device_scope.err)
+
 #define NK_CUDA(h, call)                                                     \
     do {                                                                     \
         int _rc = nk::check_cuda((h), (call), #call);                        \

@@ -79,7 +79,7 @@ int nk_lift(nk_handle *h, const double *Z, long long ldz, int m, int d, const do
     if (!Z || !inv_ls || !Sinv || !X || (!Phi && !PhiT) || m < 1 || d < 1 || N < 1 || N > 2000000000LL)
         return set_err(h, NK_E_INVALID, "nk_lift: bad argument");
     if (kind != NK_KERNEL_RBF && kind != NK_KERNEL_MATERN52) return set_err(h, NK_E_INVALID, "nk_lift: unsupported kernel kind");
-    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_ON_DEVICE(h);
     int rc;
     const int ldm = even_i(m);
     double *Kt = dense_scratch(h, 2, (size_t)N * ldm, &rc); if (rc) return rc;
@@ -99,7 +99,7 @@ int nk_predict(nk_handle *h, const double *Z, long long ldz, int m, int d, int p
     if (!Z || !inv_ls || !Sinv || !W || !X_aug || !Yhat || m < 1 || d < 1 || p < 0 || N < 1 || N > 2000000000LL)
         return set_err(h, NK_E_INVALID, "nk_predict: bad argument");
     if (kind != NK_KERNEL_RBF && kind != NK_KERNEL_MATERN52) return set_err(h, NK_E_INVALID, "nk_predict: unsupported kernel kind");
-    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_ON_DEVICE(h);
     int rc;
     const int ldm = even_i(m), ldf = even_i(m + p);
     double *Kt = dense_scratch(h, 2, (size_t)N * ldm, &rc); if (rc) return rc;
@@ -120,7 +120,7 @@ int nk_rollout(nk_handle *h, int m, int p, int d, int T, long long nb, const dou
     if (m < 1 || p < 0 || d < 1 || T < 1 || nb < 1 || nb > 2000000000LL || !A || !C || !Z0 || (p && T > 1 && (!B || !U)))
         return set_err(h, NK_E_INVALID, "nk_rollout: bad argument");
     if (Ytrue && (!sq_err || !sq_sim)) return set_err(h, NK_E_INVALID, "nk_rollout: Ytrue needs sq_err and sq_sim");
-    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_ON_DEVICE(h);
     // One persistent packed-operand GEMM per time step (nk_pgemm.cu):
     //     [ Z_{i+1} | Yhat_i ] = [ Z_i | U_i ] * [ A  B ; C  0 ]^T
     // The lifted states stay in the packed operand layout from step to step (the epilogue writes Z_{i+1} with the result
@@ -186,7 +186,7 @@ int nk_closed_loop(nk_handle *h, int m, int p, int d, int steps, long long nb, c
     cudaStream_t stream = (cudaStream_t)stream_;
     if (m < 1 || p < 1 || d < 1 || steps < 1 || nb < 1 || nb > 2000000000LL || !A || !B || !C || !K || !Z0 || !Zref || !Xs || !Us)
         return set_err(h, NK_E_INVALID, "nk_closed_loop: bad argument");
-    NK_CUDA(h, cudaSetDevice(h->device));
+    NK_ON_DEVICE(h);
     // Per step, in the reference's order of operations (benchmark_lqr_cloth.py:80-84):
     //   u_i = K (phi_ref - z_i)          packed difference (elementwise), then a p-column packed GEMM
     //   [ z_{i+1} | x_i ] = [ z_i | u_i ] [ A B ; C 0 ]^T     the rollout step of nk_rollout

@@ -81,6 +81,13 @@ class Engine:
             self._pinned = buf
         return buf
 
+    def side_stream(self):
+        """A second stream of this device for transfers that may overlap with work queued on the current stream."""
+        st = getattr(self, "_side", None)
+        if st is None:
+            st = self._side = torch.cuda.Stream(device=self.tdev)
+        return st
+
     def launch_count(self) -> int:
         return int(self.lib.nk_launch_count(self.h))
 

@@ -15,10 +15,13 @@ def shard_bounds(n_total: int, world: int, rank: int):
 
 def head_samples(m: int, d: int, p: int) -> int:
     """How many samples of fused lift+Gram work the landmark-only stage of a fit is worth (K_zz, Cholesky, 17 Newton-Schulz
-    iterations of the symmetric square root, S and S^-1: ~56 m^3 flop on the row-major GEMM at ~82% of the DMMA rate,
-    against 4m^2+6md+4mp flop per sample at ~90%).  m=4096, d=192: 63 k samples (measured: 143 ms vs 462 k samples/s)."""
+    iterations of the symmetric square root, S and S^-1: ~56 m^3 flop on the row-major GEMM at ~82% of the DMMA rate, plus the
+    packing of the three m x m results for the broadcast, against 4m^2+6md+4mp flop per sample at ~90%).  Calibrated on the
+    measurement at m=4096, d=192: 143 ms against 467 k samples/s = 67 k samples (the pure flop model, coefficient 56, gave 59 k and
+    left the other ranks waiting ~17 ms for the head).  Overshooting is cheap (the surplus is spread over the other ranks),
+    undershooting is paid in full."""
     per_sample = 4.0 * m * m + 6.0 * m * d + 4.0 * m * p
-    return int(56.0 * m ** 3 / per_sample * (0.90 / 0.82))
+    return int(64.0 * m ** 3 / per_sample * (0.90 / 0.82))
 
 
 def balanced_bounds(n_total: int, world: int, rank: int, head: int = 0, head_rank: int = 0):

@@ -71,8 +71,12 @@ def test_two_devices_in_one_process():
     Z = Y[rng.choice(n, m, replace=False)]
     ls = np.full(d, 2.0)
     ref = O.grams(Xs, Y, U, Z, O.RBF, ls)
+    before = torch.cuda.current_device()
     for devno in (0, 1):
         eng = Engine.get(devno)
+        # the library runs on its handle's device and must leave the CALLER's current device alone (it used to leave the
+        # handle's device selected: the next `.cuda()` of the caller then landed on the wrong GPU)
+        assert torch.cuda.current_device() == before
         with torch.cuda.device(devno):
             t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=f"cuda:{devno}")
             G = eng.grams(t(np.hstack((Xs, U))), t(Y), t(Z), t(1.0 / ls), O.RBF, p)
@@ -84,3 +88,10 @@ def test_two_devices_in_one_process():
             z0 = t(rng.standard_normal((3, m)))
             out = eng.rollout(t(rng.standard_normal((m, m)) * 0.1), None, t(rng.standard_normal((d, m))), z0, None, Ytrue=t(rng.standard_normal((1, 3, d))))
             assert out["Yhat"].shape == (1, 3, d)
+        assert torch.cuda.current_device() == before
+    # a handle of another device driven WITHOUT a torch device guard around the calls: still no change of the current device
+    eng1 = Engine.get(1)
+    t1 = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda:1")
+    K1 = eng1.kzz(t1(Z), t1(1.0 / ls), O.RBF)
+    assert K1.device.index == 1 and torch.cuda.current_device() == before
+    assert O.relerr(K1.cpu().numpy(), O.kernel_matrix(Z, Z, O.RBF, ls)) <= 1e-13
