@@ -7,7 +7,9 @@
  *   - all matrix pointers are CALLER-OWNED DEVICE pointers to IEEE float64, row-major with an explicit
  *     leading dimension (elements) unless a parameter is documented as "host".
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); asynchronous failures
- *     surface at the next synchronising call.  A handle is bound to one device and is not thread-safe.
+ *     surface at the next synchronising call.  A handle is bound to one device and is not thread-safe; every call runs
+ *     on the handle's device and restores the caller's current CUDA device before it returns (streams and pointers passed
+ *     in must belong to the handle's device).
  *   - there is NO CPU fallback: every function fails with NK_E_CUDA when no sm_100 device is usable.
  */
 #ifndef NK_B200_H
