@@ -50,6 +50,13 @@ int nk_gram_update(nk_handle *h, const double *X, long long ldx, const double *Y
 int nk_gram_finalize(nk_handle *h, double *Gxx, long long ld_gxx, double *Gyx, long long ld_gyx,
                      double *Gyy, long long ld_gyy, double *Gxu, long long ld_gxu, double *Gyu, long long ld_gyu,
                      double *Guu, long long ld_guu, double *GYy, long long ld_gYy, int accumulate, void *stream);
+/* Introspection, HOST ONLY (no device needed): the work plan nk_gram_begin builds for these sizes on a GPU with sm_count SMs.
+ * summary[12] = {chunk, MP, KLS, EP, psi_rows, nblk, ntiles, n_pack, n_lift, n_gram, period_len, nslots};  items (may be NULL)
+ * receives up to items_cap entries of ONE period of the global work order, 4 ints each {type (0 pack, 1 lift, 2 Gram tile), a, b, c}
+ * (pack: a = 128-sample strip; lift: a = side, b = landmark block, c = strip; Gram: a, b = row blocks of Psi, c = accumulator tile).
+ * Period k holds the Gram items of chunk k and the pack / lift items of chunk k+1.  Returns period_len (<0: invalid argument).
+ * tests/test_gram_plan.py checks on the CPU that every item depends only on items earlier in the claim order. */
+int nk_gram_plan(int m, int d, int p, int chunk, int sm_count, int *summary, int *items, int items_cap);
 /* executed FP64 flops of the last update (for roofline accounting), and launches issued so far */
 double nk_gram_last_executed_flops(nk_handle *h);
 long long nk_launch_count(nk_handle *h);

@@ -50,6 +50,72 @@ __global__ void __launch_bounds__(256) dmma_probe_kernel(double *out, int iters,
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// ---- the work plan of the fused engine (pure host code: no device needed; also exported as nk_gram_plan for the CPU tests) ----
+struct GramPlan {
+    int chunk, MP, KLS, EP, psi_rows, nblk, ntiles, n_sy, n_pk, n_lf, nslots;
+    std::vector<GramItem> period;     // one period of the global work order
+    std::vector<int> tile_of;         // (nblk x nblk) block pair -> accumulator tile, -1 where nothing is accumulated
+};
+
+void plan_gram(int m, int d, int p, int chunk, int sm_count, GramPlan &P) {
+    if (chunk <= 0) chunk = 512;
+    chunk = ((chunk + kTile - 1) / kTile) * kTile;
+    P.chunk = chunk;
+    P.MP = ((m + kTile - 1) / kTile) * kTile;
+    P.KLS = (d + 2 + kSlabK - 1) / kSlabK;
+    P.EP = ((p + d + kTile - 1) / kTile) * kTile;
+    P.psi_rows = 2 * P.MP + P.EP;
+    const int MB = P.MP / kTile, EB = P.EP / kTile;
+    P.nblk = 2 * MB + EB;
+
+    // ---- accumulator tiles: lower triangle over the feature blocks, plus the [U;Y] products the fit needs ----
+    std::vector<GramItem> sy;
+    P.tile_of.assign((size_t)P.nblk * P.nblk, -1);
+    auto add_tile = [&](int I, int J) {
+        const int t = (int)sy.size();
+        P.tile_of[(size_t)I * P.nblk + J] = t;
+        sy.push_back(GramItem{kItemSyrk, I, J, t});
+    };
+    for (int I = 0; I < 2 * MB; I++) for (int J = 0; J <= I; J++) add_tile(I, J);
+    const int u_blocks = (p + kTile - 1) / kTile;                 // E blocks holding control rows (0 or 1)
+    for (int e = 0; e < EB; e++) {
+        for (int J = 0; J < 2 * MB; J++) {
+            const bool is_x = J < MB;
+            if (is_x && e >= u_blocks) continue;                  // Y x Phi_x is not needed (regressors.py:164 pairs Y with Phi_y)
+            add_tile(2 * MB + e, J);
+        }
+    }
+    for (int e = 0; e < u_blocks; e++) for (int f = 0; f <= e; f++) add_tile(2 * MB + e, 2 * MB + f);   // U U^T
+    P.ntiles = (int)sy.size();
+    P.n_sy = P.ntiles;
+    P.n_pk = chunk / kTile;
+    P.n_lf = 2 * MB * (chunk / kTile);
+
+    // ---- one period of the global work order: syrk(c) with pack(c+1) at 1/4 and lift(c+1) at 1/2 ----
+    // Every item depends only on items EARLIER in this order (pack(c) <- syrk(c-S); lift(c) <- pack(c); syrk(c) <- lift(c) and
+    // the same tile of syrk(c-1)): with all CTAs resident and claiming in order, nobody can wait for an unclaimed item.
+    P.period.clear();
+    const int q1 = P.n_sy / 4, q2 = P.n_sy / 2;
+    for (int i = 0; i < q1; i++) P.period.push_back(sy[i]);
+    for (int sb = 0; sb < P.n_pk; sb++) P.period.push_back(GramItem{kItemPack, sb, 0, 0});
+    for (int i = q1; i < q2; i++) P.period.push_back(sy[i]);
+    for (int sb = 0; sb < chunk / kTile; sb++)
+        for (int side = 0; side < 2; side++)
+            for (int lb = 0; lb < MB; lb++) P.period.push_back(GramItem{kItemLift, side, lb, sb});
+    for (int i = q2; i < P.n_sy; i++) P.period.push_back(sy[i]);
+
+    // Chunks in flight.  With many landmarks one chunk's items (thousands of Gram tiles) fill the GPU and two buffers suffice;
+    // with few (the script configurations: m = 10 ... 400 gives 18 ... 150 items per chunk) the persistent CTAs would idle
+    // behind the pack -> lift -> Gram chain of a single chunk, so several chunks are kept in flight (one buffer set each).
+    const int period_len = (int)P.period.size();
+    P.nslots = 2;
+    if (period_len < 2 * sm_count) {
+        P.nslots = (3 * sm_count + period_len - 1) / period_len;
+        P.nslots = std::min(std::max(P.nslots, 2), kMaxSlots);
+    }
+}
+
 }  // namespace nk
 
 using namespace nk;
@@ -137,6 +203,19 @@ int nk_probe_dmma_tflops(nk_handle *h, double ms_target, double *tflops) {
     return NK_OK;
 }
 
+int nk_gram_plan(int m, int d, int p, int chunk, int sm_count, int *summary, int *items, int items_cap) {
+    if (m < 1 || d < 1 || p < 0 || p > kTile || sm_count < 1 || !summary) return NK_E_INVALID;
+    GramPlan P;
+    plan_gram(m, d, p, chunk, sm_count, P);
+    const int vals[12] = {P.chunk, P.MP, P.KLS, P.EP, P.psi_rows, P.nblk, P.ntiles, P.n_pk, P.n_lf, P.n_sy, (int)P.period.size(), P.nslots};
+    for (int i = 0; i < 12; i++) summary[i] = vals[i];
+    if (items) {
+        const int n = std::min((int)P.period.size(), items_cap);
+        for (int i = 0; i < n; i++) { items[4 * i] = P.period[i].type; items[4 * i + 1] = P.period[i].a; items[4 * i + 2] = P.period[i].b; items[4 * i + 3] = P.period[i].c; }
+    }
+    return (int)P.period.size();
+}
+
 int nk_gram_begin(nk_handle *h, const double *Z, long long ldz, int m, int d, int p, const double *inv_ls, int kind,
                   int chunk, void *stream_) {
     if (!h) return NK_E_INVALID;
@@ -145,58 +224,16 @@ int nk_gram_begin(nk_handle *h, const double *Z, long long ldz, int m, int d, in
     if (kind != NK_KERNEL_RBF && kind != NK_KERNEL_MATERN52) return set_err(h, NK_E_INVALID, "nk_gram_begin: unsupported kernel kind");
     if (p > kTile) return set_err(h, NK_E_INVALID, "nk_gram_begin: more than 128 control inputs are not supported");
     NK_ON_DEVICE(h);
-    if (chunk <= 0) chunk = 512;
-    chunk = ((chunk + kTile - 1) / kTile) * kTile;
+    GramPlan plan;
+    plan_gram(m, d, p, chunk, h->sm_count, plan);
+    chunk = plan.chunk;
     h->m = m; h->d = d; h->p = p; h->kind = kind; h->nk_chunk = chunk;
-    h->MP = ((m + kTile - 1) / kTile) * kTile;
-    h->KLS = (d + 2 + kSlabK - 1) / kSlabK;
-    h->EP = ((p + d + kTile - 1) / kTile) * kTile;
-    h->psi_rows = 2 * h->MP + h->EP;
-    const int MB = h->MP / kTile, EB = h->EP / kTile;
-    h->nblk = 2 * MB + EB;
-
-    // ---- accumulator tiles: lower triangle over the feature blocks, plus the [U;Y] products the fit needs ----
-    std::vector<GramItem> sy;
-    h->h_tile_of.assign((size_t)h->nblk * h->nblk, -1);
-    auto add_tile = [&](int I, int J) {
-        const int t = (int)sy.size();
-        h->h_tile_of[(size_t)I * h->nblk + J] = t;
-        sy.push_back(GramItem{kItemSyrk, I, J, t});
-    };
-    for (int I = 0; I < 2 * MB; I++) for (int J = 0; J <= I; J++) add_tile(I, J);
-    const int u_blocks = (p + kTile - 1) / kTile;                 // E blocks holding control rows (0 or 1)
-    for (int e = 0; e < EB; e++) {
-        for (int J = 0; J < 2 * MB; J++) {
-            const bool is_x = J < MB;
-            if (is_x && e >= u_blocks) continue;                  // Y x Phi_x is not needed (regressors.py:164 pairs Y with Phi_y)
-            add_tile(2 * MB + e, J);
-        }
-    }
-    for (int e = 0; e < u_blocks; e++) for (int f = 0; f <= e; f++) add_tile(2 * MB + e, 2 * MB + f);   // U U^T
-    h->ntiles = (int)sy.size();
-    h->n_sy = h->ntiles;
-    h->n_pk = chunk / kTile;
-    h->n_lf = 2 * MB * (chunk / kTile);
-
-    // ---- one period of the global work order: syrk(c) with pack(c+1) at 1/4 and lift(c+1) at 1/2 ----
-    std::vector<GramItem> period;
-    const int q1 = h->n_sy / 4, q2 = h->n_sy / 2;
-    for (int i = 0; i < q1; i++) period.push_back(sy[i]);
-    for (int sb = 0; sb < h->n_pk; sb++) period.push_back(GramItem{kItemPack, sb, 0, 0});
-    for (int i = q1; i < q2; i++) period.push_back(sy[i]);
-    for (int sb = 0; sb < chunk / kTile; sb++)
-        for (int side = 0; side < 2; side++)
-            for (int lb = 0; lb < MB; lb++) period.push_back(GramItem{kItemLift, side, lb, sb});
-    for (int i = q2; i < h->n_sy; i++) period.push_back(sy[i]);
-    h->period_len = (int)period.size();
-    // Chunks in flight.  With many landmarks one chunk's items (thousands of Gram tiles) fill the GPU and two buffers suffice;
-    // with few (the script configurations: m = 10 ... 400 gives 18 ... 150 items per chunk) the persistent CTAs would idle
-    // behind the pack -> lift -> Gram chain of a single chunk, so several chunks are kept in flight (one buffer set each).
-    h->nslots = 2;
-    if (h->period_len < 2 * h->sm_count) {
-        h->nslots = (3 * h->sm_count + h->period_len - 1) / h->period_len;
-        h->nslots = std::min(std::max(h->nslots, 2), kMaxSlots);
-    }
+    h->MP = plan.MP; h->KLS = plan.KLS; h->EP = plan.EP; h->psi_rows = plan.psi_rows; h->nblk = plan.nblk;
+    h->h_tile_of = plan.tile_of;
+    h->ntiles = plan.ntiles; h->n_sy = plan.n_sy; h->n_pk = plan.n_pk; h->n_lf = plan.n_lf;
+    h->period_len = (int)plan.period.size();
+    h->nslots = plan.nslots;
+    const std::vector<GramItem> &period = plan.period;
 
     int rc;
     if ((rc = ensure(h, h->zp, (size_t)h->MP * h->KLS * kSlabK * 8)) != NK_OK) return rc;
