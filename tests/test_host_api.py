@@ -131,3 +131,31 @@ def test_c_abi_fails_loudly_without_device():
 def test_out_of_scope_baselines_are_importable():
     import regressors as R
     assert isinstance(R.KoopmanSplineRegressor, type) and isinstance(R.KoopmanKernelRegressor, type)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/nk_b200.h is the drop-in boundary: it must compile as plain C99 (no C++ / torch types in the signatures) and a C
+    program must link against libnkb200.so.  Without a GPU nk_create fails with NK_E_CUDA and says why (no CPU fallback)."""
+    import shutil
+    import subprocess
+    from nys_koop_lqr_b200 import _lib, build
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    build.build()
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "nk_b200.h"\n'
+        'int main(void) { nk_handle *h = 0; int rc = nk_create(&h, 0);\n'
+        '  if (rc != NK_OK) { printf("%d %s\\n", rc, nk_last_error_string(0)); return 3; }\n'
+        '  printf("ok %d SMs, ABI %d\\n", nk_device_sm_count(h), nk_version()); return nk_destroy(h); }\n')
+    exe = tmp_path / "abi"
+    libdir = _lib.LIB_PATH.parent
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", str(ROOT / "include"), str(src), "-o", str(exe),
+                    "-L", str(libdir), "-lnkb200", f"-Wl,-rpath,{libdir}"], check=True, capture_output=True, text=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    import torch
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and r.stdout.startswith("ok ")
+    else:
+        assert r.returncode == 3 and r.stdout.startswith("-2 ") and "no CPU fallback" in r.stdout
