@@ -112,14 +112,15 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------
 def cpu_rate(n_sample, m, d, p, seed=0):
     """Times the n-proportional stage of the reference fit (kernel lift via scipy cdist, as sklearn's kernels do, plus the
-    Gram dgemms of regressors.py:141-142,147,151,153,162,164) on n_sample samples.  Returns (samples/s, seconds)."""
+    Gram dgemms of regressors.py:141-142,147,151,153,162,164) on n_sample samples, with every host thread: OpenBLAS threads
+    for the dgemms and a thread pool over sample strips for cdist (the reference itself runs cdist on ONE thread, so this
+    is the faster of the two).  Returns (samples/s, seconds)."""
     from oracle import nk_oracle as O
     Xs, U, Y = O.synthetic(max(n_sample, m), d, p, seed=seed)
     np.random.seed(0)
     Z = O.draw_landmarks(Y, m)
     Xs, U, Y = Xs[:n_sample], U[:n_sample], Y[:n_sample]
-    # all host threads for the BLAS part, also when a launcher (torchrun) exported OMP_NUM_THREADS=1 before numpy was loaded;
-    # scipy's cdist is single-threaded by construction (SURVEY 3.1), exactly as in the reference
+    # all host threads for the BLAS part, also when a launcher (torchrun) exported OMP_NUM_THREADS=1 before numpy was loaded
     try:
         from threadpoolctl import threadpool_limits
         ctx = threadpool_limits(limits=os.cpu_count())
@@ -128,9 +129,40 @@ def cpu_rate(n_sample, m, d, p, seed=0):
         ctx = contextlib.nullcontext()
     with ctx:
         t0 = time.perf_counter()
-        O.grams(Xs, Y, U, Z, O.RBF, np.full(d, 10.0), chunk=n_sample)
+        O.grams(Xs, Y, U, Z, O.RBF, np.full(d, 10.0), chunk=n_sample, threads=os.cpu_count() or 1)
         dt = time.perf_counter() - t0
     return n_sample / dt, dt
+
+
+def unmodified_reference_fit(d, p, m_ref=1024, sizes=(4000, 20000)):
+    """SURVEY 8(d): the UNMODIFIED reference (baseline/_ref/regressors.py, installed from /root/reference by
+    tools/stage_reference.sh) timed on the host: KoopmanNystromRegressor.fit at n in `sizes`, fitted to T(n) = T0 + n / r.
+    m = 4096 costs ~420 s per fit (two scipy sqrtm of 138 s each, SURVEY 3.1), so the in-bench fit runs at m_ref landmarks and the
+    m = 4096 figures of SURVEY 3.1 are quoted beside it.  Returns None when baseline/_ref is not on this box."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    path = os.path.join(ref_dir, "regressors.py")
+    if not os.path.exists(path):
+        return None
+    import importlib.util
+    from oracle import nk_oracle as O
+    spec = importlib.util.spec_from_file_location("_nk_unmodified_reference", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    times = []
+    for n in sizes:
+        Xs, U, Y = O.synthetic(n, d, p, seed=7)
+        np.random.seed(0)
+        reg = mod.KoopmanNystromRegressor(p, kernel=mod.ThreeDimensionalKernel(10, 10, 10, d), gamma=1e-4, m=m_ref)
+        t0 = time.perf_counter()
+        reg.fit(np.hstack((Xs, U)), Y)
+        times.append(time.perf_counter() - t0)
+    (n0, n1), (t0_, t1_) = sizes, times
+    r = (n1 - n0) / max(t1_ - t0_, 1e-9)
+    T0 = t0_ - n0 / r
+    return {"m": m_ref, "d": d, "p": p, "n": list(sizes), "fit_s": [round(t, 3) for t in times], "r_samples_per_s": r, "T0_s": T0,
+            "naive_samples_per_s": n1 / t1_,
+            "note": "unmodified baseline/_ref/regressors.py::KoopmanNystromRegressor.fit, T(n) = T0 + n/r; at m=4096 the same code measured "
+                    "T0 ~ 365 s and r ~ 365 samples/s on 8 vCPU (SURVEY 3.1: 424 s at n=20000) -- too long to repeat inside the bench"}
 
 
 def run_reference_arm(args):
@@ -146,15 +178,19 @@ def run_reference_arm(args):
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = n_sample / (ms * 1e-3)
+    unmod = None if args.no_ref_fit else unmodified_reference_fit(d, p)
     sample = (f"{n_sample} of the {args.n} samples per step, m={m}, d={d}: the n-proportional stage of the reference fit (cdist kernel lift "
-              f"+ 7 Gram dgemms, regressors.py:141-164) restated in oracle/nk_oracle.py with the same scipy/numpy calls; the reference's "
-              f"n-independent stage (2 sqrtm + 2 lstsq + 2 solve, ~365 s at m=4096 in SURVEY 3.1) is excluded, which overstates the CPU "
-              f"rate at n=1e7 by <2%; the unmodified reference cannot run n=1e7 (3 x 327 GB of m x n matrices)")
+              f"+ 7 Gram dgemms, regressors.py:141-164) restated in oracle/nk_oracle.py with the same scipy/numpy calls, cdist spread over "
+              f"{os.cpu_count()} threads (the reference runs it on one).  The reference's n-independent stage (2 sqrtm + 2 lstsq + 2 solve, "
+              f"T0 ~ 365 s at m=4096 in SURVEY 3.1) is excluded from the per-step time: at n=1e7 that overstates the CPU rate by "
+              f"T0 / (n / r) ~ 365 / {args.n / value:.0f} s.  The unmodified reference cannot run n=1e7 (3 x 327 GB of m x n matrices); its own "
+              f"fit is timed once per run at m=1024 in `unmodified_reference`")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "_ref+port" if unmod else "port", "sample": sample,
+                         "unmodified_reference": unmod},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -196,6 +232,58 @@ def generate_shard(torch, dev, n_local, d, p, seed, pinned):
         Yh = torch.empty(n_local, d, dtype=torch.float64, pin_memory=True)
         Xh.copy_(X); Yh.copy_(Y)
     return X, Y, Xh, Yh
+
+
+def parity_check(args, eng, R, kernel, world, rank, dist, torch):
+    """SURVEY 8(d): ONE numpy-generated prefix (oracle/nk_oracle.py::synthetic) is fed to both implementations before the timed
+    region, at the bench's own (m, d, p, gamma) -- the same fused-kernel instantiation the timed fit runs.  The seven Grams are
+    compared element-wise with the oracle's (scipy cdist + dgemm); A / B / C / weights with the oracle's eigh + Cholesky
+    statement of regressors.py:147-169.  `floor` is how far the ORACLE's own A / B / C move when its Grams are summed in another
+    chunk order (cond(inner_term) ~ 5e7 at gamma = 1e-4): the A/B/C gate is max(1e-9, 3 floor).  Under torchrun the estimator
+    path is fit_distributed on the sharded prefix (allreduce and sharded solve included); rank 0 runs the oracle."""
+    from nys_koop_lqr_b200 import sharding
+    from oracle import nk_oracle as O
+    m, d, p = args.m, args.d, args.p
+    n = max(int(args.parity_samples), m)
+    Xs, U, Y = O.synthetic(n, d, p, seed=2024)
+    np.random.seed(0)
+    Z = O.draw_landmarks(Y, m)
+    X = np.hstack((Xs, U))
+    reg = R.KoopmanNystromRegressor(p, kernel=kernel, gamma=args.gamma, m=m)
+    reg.nystrom_centers_output = np.ascontiguousarray(Z.T)
+    t0 = time.perf_counter()
+    if world > 1:
+        off, cnt = sharding.shard_bounds(n, world, rank)
+        reg.fit_distributed(torch.from_numpy(X[off:off + cnt]).to(eng.tdev), torch.from_numpy(Y[off:off + cnt]).to(eng.tdev))
+    else:
+        reg.fit(X, Y)
+    gpu_s = time.perf_counter() - t0
+    out = None
+    if rank == 0:
+        dev_ = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(eng.tdev)
+        G = eng.grams(dev_(X), dev_(Y), dev_(Z), dev_(np.full(d, 0.1)), 0, p)
+        summ = eng.gram_plan(m, d, p)
+        t0 = time.perf_counter()
+        ls = np.full(d, 10.0)
+        thr = os.cpu_count() or 1
+        ref = O.grams(Xs, Y, U, Z, O.RBF, ls, chunk=n, threads=thr)
+        ref2 = O.grams(Xs, Y, U, Z, O.RBF, ls, chunk=1024, threads=thr)
+        Kzz = O.kernel_matrix(Z, Z, O.RBF, ls)
+        want = O.solve_abc(ref, Kzz, args.gamma * n, solver="chol")
+        want2 = O.solve_abc(ref2, Kzz, args.gamma * n, solver="chol")
+        floor = max(O.relerr(a, b) for a, b in zip(want2, want))
+        errs = {k: O.relerr(G[k].cpu().numpy(), ref[k]) for k in ("Gxx", "Gyx", "Gyy", "Gxu", "Gyu", "Guu", "GYy")}
+        abc = {k: O.relerr(g, w) for k, g, w in zip("ABCW", (reg.A, reg.B, reg.C, reg.weights), want)}
+        gate_abc = max(1e-9, 3.0 * floor)
+        out = {"n_prefix": n, "G": max(errs.values()), "A": abc["A"], "B": abc["B"], "C": abc["C"], "W": abc["W"],
+               "gate_G": 1e-12, "gate_ABC": gate_abc, "oracle_floor": floor,
+               "ok": bool(max(errs.values()) <= 1e-12 and max(abc.values()) <= gate_abc),
+               "gram_kernel_nslots": summ["nslots"], "grams": errs, "oracle_s": round(time.perf_counter() - t0, 1), "gpu_fit_s": round(gpu_s, 3),
+               "against": "oracle/nk_oracle.py (grams: scipy cdist + dgemm; solve_abc(solver='chol')) on the same numpy prefix, "
+                          "reference regressors.py:141-167"}
+    if world > 1:
+        dist.barrier()
+    return out
 
 
 def run_gpu_arm(args):
@@ -274,7 +362,24 @@ def run_gpu_arm(args):
         launches = eng.launch_count() - l0
         return ms, launches, reg
 
+    parity = None if args.no_parity else parity_check(args, eng, R, kernel, world, rank, dist, torch)
     peak_tflops = eng.probe_dmma_tflops(300.0)                    # FP64 tensor roofline denominator, measured here
+    # second, independent denominator: the vendor library's FP64 GEMM on this GPU, this run (8192^3, best of 5)
+    peak_dgemm = None
+    try:
+        a_ = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+        b_ = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+        best = float("inf")
+        for i in range(6):
+            t0_, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0_.record(); c_ = a_ @ b_; t1_.record(); torch.cuda.synchronize()
+            if i:
+                best = min(best, t0_.elapsed_time(t1_))
+        peak_dgemm = 2.0 * 8192.0 ** 3 / (best * 1e-3) * 1e-12
+        del a_, b_, c_
+        torch.cuda.empty_cache()
+    except Exception as exc:  # noqa: BLE001
+        print(f"bench.py: torch.matmul FP64 probe failed: {exc}", file=sys.stderr)
     with ClockSampler(local_rank) as cs:
         ms_step, launches, reg = timed(X, Y, args.steps, args.warmup, collect=True)
     clocks = cs.summary()
@@ -303,7 +408,8 @@ def run_gpu_arm(args):
             r, dt = cpu_rate(args.cpu_sample, m, d, p)
             cpu = {"value": r, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                    "sample": f"{args.cpu_sample} samples at m={m}, d={d}: n-proportional stage of the reference fit (scipy cdist lift + Gram dgemms) "
-                             f"via oracle/nk_oracle.py, {dt:.1f} s; the n-independent stage (~365 s at m=4096 in the reference) is excluded"}
+                             f"via oracle/nk_oracle.py with cdist on {os.cpu_count()} threads, {dt:.1f} s; the n-independent stage (~365 s at m=4096 in "
+                             f"the reference) is excluded; `bench.py --impl reference` also times the unmodified baseline/_ref fit"}
         traffic = None
         tnote = "no ncu capture recorded yet"
         try:
@@ -322,11 +428,13 @@ def run_gpu_arm(args):
                          "kernel": "nk::gram_kernel (fused kernel lift + Gram, FP64 DMMA)", "kernel_ms": kernel_ms,
                          "algorithmic_flops_per_sample": F, "samples_per_launch": float(np.mean(k_n)) if k_n else None,
                          "peak_source": "register-only DMMA.8x8x4 issue-rate probe (nk_probe_dmma_tflops) run on this GPU just before the timed region; "
-                                        "MEASURED_PEAKS.json has no FP64 entry; cuBLAS DGEMM 8192^3 on this pool: 35.4 TFLOP/s, nominal 40",
+                                        "MEASURED_PEAKS.json has no FP64 entry; peak_dgemm = torch.matmul FP64 8192^3 (cuBLAS) measured in this run",
+                         "peak_dgemm": peak_dgemm, "frac_dgemm": (achieved / peak_dgemm) if (achieved and peak_dgemm) else None,
                          "whole_fit_frac": F * n / world / (ms_step * 1e-3) * 1e-12 / peak_tflops, "traffic_note": tnote,
                          "peak_nominal": 40.0, "frac_nominal": (achieved / 40.0) if achieved else None,
-                         "nominal_note": "NVIDIA's B200 FP64 tensor figure (40 TFLOP/s); the DMMA issue rate measured on this pool is 37.1"},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                         "nominal_note": "NVIDIA's B200 FP64 tensor figure (40 TFLOP/s); the DMMA issue rate measured on this pool is 37.1",
+                         "gpu_launches_note": "gpu_launches = kernels of libnkb200.so launched per step (one fit), counted by the handle"},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(round(launches / max(args.steps, 1))), "clocks": clocks, "parity": parity,
             "model_check": {"A_shape": list(reg.A.shape), "A_fro": float(np.linalg.norm(reg.A)), "finite": bool(np.isfinite(reg.A).all() and np.isfinite(reg.C).all())},
         }
         emit(line)
@@ -351,6 +459,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ref-fit", action="store_true", help="reference arm: skip the one unmodified baseline/_ref fit")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity check on a numpy prefix before the timed region")
+    ap.add_argument("--parity-samples", type=int, default=8192)
     args = ap.parse_args()
     protect_stdout()
     if args.impl == "reference":

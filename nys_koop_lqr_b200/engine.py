@@ -42,6 +42,28 @@ class Engine:
         self.h = h
         self.tdev = torch.device("cuda", self.device)
         self.gram_events = None   # set to [] to collect (start, end, n) CUDA-event triples per fused-kernel launch
+        self._warm()
+
+    def _warm(self):
+        """One tiny fit-shaped pass through every stage, so that the one-off costs of a process (lazy loading of the kernels
+        into the context, opt-in shared-memory attributes, the cooperative-launch occupancy query, first workspace
+        allocations) are paid when the engine is created and not inside the caller's first `fit` (it measured 3.1 s there)."""
+        with torch.cuda.device(self.tdev):
+            g = torch.Generator(device=self.tdev); g.manual_seed(0)
+            n, d, p, m = 300, 3, 1, 24
+            X = torch.randn(n, d + p, dtype=torch.float64, device=self.tdev, generator=g)
+            Y = torch.randn(n, d, dtype=torch.float64, device=self.tdev, generator=g)
+            Z = Y[:m].contiguous()
+            il = torch.ones(d, dtype=torch.float64, device=self.tdev)
+            G = self.grams(X, Y, Z, il, NK_KERNEL_RBF, p)
+            Kzz = self.kzz(Z, il, NK_KERNEL_RBF)
+            Kmm = Kzz.clone(); Kmm.diagonal().add_(JITTER)
+            S, Sinv = self.sym_sqrt(Kmm)
+            A, B, Cm, W = self.solve_abc(G, Kzz, S, Sinv, 1e-2 * n)
+            self.predict(Z, il, NK_KERNEL_RBF, Sinv, W, X[:8], p)
+            Z0 = self.lift(Z, il, NK_KERNEL_RBF, Sinv, X[:4, :d].contiguous(), transposed=True)
+            self.rollout(A, B, Cm, Z0, torch.zeros(2, 4, p, dtype=torch.float64, device=self.tdev))
+            torch.cuda.synchronize(self.tdev)
 
     @classmethod
     def get(cls, device: int | None = None) -> "Engine":
@@ -159,6 +181,15 @@ class Engine:
         self.gram_begin(Z, inv_ls, kind, p, chunk)
         self.gram_update(X_aug, Y)
         return self.gram_finalize()
+
+    def gram_plan(self, m, d, p, chunk=0):
+        """The work plan nk_gram_begin builds for these sizes on this GPU (host-only introspection, include/nk_b200.h)."""
+        summ = (C.c_int * 12)()
+        rc = self.lib.nk_gram_plan(int(m), int(d), int(p), int(chunk), self.sm_count(), summ, None, 0)
+        if rc < 0:
+            raise ValueError("nk_gram_plan: invalid sizes")
+        keys = ("chunk", "MP", "KLS", "EP", "psi_rows", "nblk", "ntiles", "n_pack", "n_lift", "n_gram", "period_len", "nslots")
+        return dict(zip(keys, [int(v) for v in summ]))
 
     def gram_executed_flops(self) -> float:
         return float(self.lib.nk_gram_last_executed_flops(self.h))

@@ -61,29 +61,47 @@ def kernel_matrix(A_rows, B_rows, kind, length_scale):
 # --------------------------------------------------------------------------------------------
 # the seven data-sample Grams  (regressors.py:147,151,153,162,164)
 # --------------------------------------------------------------------------------------------
-def grams(Xs, Y, U, Z, kind, length_scale, chunk=8192):
+def grams(Xs, Y, U, Z, kind, length_scale, chunk=8192, threads=1):
     """Xs (n,d) states, Y (n,d) next states, U (n,p) controls, Z (m,d) landmarks.
 
     Returns dict: Gxx = Phi_x Phi_x' (m,m), Gyx = Phi_y Phi_x' (m,m), Gyy (m,m), Gxu = Phi_x U (m,p),
     Gyu (m,p), Guu (p,p), GYy = Y' Phi_y' (d,m); Phi_x = k(Z, Xs) (m,n), Phi_y = k(Z, Y).
     Chunked over samples so n*m never has to exist (the reference materialises it; the sums are the same).
+    threads > 1: the kernel lifts of a chunk (scipy cdist releases the GIL) are computed by a thread pool over column
+    strips -- same arithmetic per entry, so the result is bit-identical to threads=1; only the wall time changes (the
+    reference itself runs cdist on one thread; the CPU baseline of bench.py says which it timed).
     """
     n, d = Xs.shape
     m, p = Z.shape[0], U.shape[1]
     G = dict(Gxx=np.zeros((m, m)), Gyx=np.zeros((m, m)), Gyy=np.zeros((m, m)), Gxu=np.zeros((m, p)),
              Gyu=np.zeros((m, p)), Guu=np.zeros((p, p)), GYy=np.zeros((d, m)))
-    for s in range(0, n, chunk):
-        e = min(n, s + chunk)
-        Px = kernel_matrix(Z, Xs[s:e], kind, length_scale)
-        Py = kernel_matrix(Z, Y[s:e], kind, length_scale)
-        Uc, Yc = U[s:e], Y[s:e]
-        G["Gxx"] += Px @ Px.T
-        G["Gyx"] += Py @ Px.T
-        G["Gyy"] += Py @ Py.T
-        G["Gxu"] += Px @ Uc
-        G["Gyu"] += Py @ Uc
-        G["Guu"] += Uc.T @ Uc
-        G["GYy"] += Yc.T @ Py.T
+    pool = None
+    if threads and threads > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(int(threads))
+
+    def lifted(rows):
+        if pool is None or rows.shape[0] < 2 * threads:
+            return kernel_matrix(Z, rows, kind, length_scale)
+        cuts = np.linspace(0, rows.shape[0], int(threads) + 1).astype(int)
+        parts = list(pool.map(lambda i: kernel_matrix(Z, rows[cuts[i]:cuts[i + 1]], kind, length_scale), range(int(threads))))
+        return np.hstack(parts)
+    try:
+        for s in range(0, n, chunk):
+            e = min(n, s + chunk)
+            Px = lifted(Xs[s:e])
+            Py = lifted(Y[s:e])
+            Uc, Yc = U[s:e], Y[s:e]
+            G["Gxx"] += Px @ Px.T
+            G["Gyx"] += Py @ Px.T
+            G["Gyy"] += Py @ Py.T
+            G["Gxu"] += Px @ Uc
+            G["Gyu"] += Py @ Uc
+            G["Guu"] += Uc.T @ Uc
+            G["GYy"] += Yc.T @ Py.T
+    finally:
+        if pool is not None:
+            pool.shutdown()
     return G
 
 
@@ -255,6 +273,28 @@ def cv_scores(X_aug, Y, n_inputs, kinds_ls, gammas, Z, n_splits=5, solver="chol"
                 f = fit(X_aug[tr], Y[tr], n_inputs, kind, ls, gamma, Z=Z, solver=solver)
                 out[ki, gi, fi] = neg_rmse(Y[s:e], predict(f["W"], Z, X_aug[s:e], n_inputs, kind, ls, solver))
     return out
+
+
+def cv_weights(G, Kzz, gamma_n):
+    """Prediction weights in kernel-matrix coordinates, Wk (d, m+p), such that regressors.py:48-55 reads
+    Yhat = Wk [k(Z,x); u].  With weights = C G_ls (regressors.py:167) and lift = S^-1 k(Z,x) (:171-178) the symmetric square
+    roots cancel:  Wk = [V_phi Kzz Kmm^-1 | V_u],  V = GYy inner_rec^-1 [Gyx|Gyu] inner^-1  (inner / inner_rec of :151,:162),
+    so that large landmark counts need no eigen-decomposition.  tests/test_oracle_golden.py::test_cv_weights_identity checks this
+    algebra against `solve_abc` + `lift`."""
+    m = Kzz.shape[0]
+    p = G["Guu"].shape[0]
+    Kmm = Kzz + JITTER * np.eye(m)
+    inner = np.empty((m + p, m + p))
+    inner[:m, :m] = G["Gxx"] + gamma_n * Kmm
+    inner[:m, m:] = G["Gxu"]
+    inner[m:, :m] = G["Gxu"].T
+    inner[m:, m:] = G["Guu"] + gamma_n * np.eye(p)
+    cross = np.hstack((G["Gyx"], G["Gyu"]))
+    inner_rec = gamma_n * Kmm + G["Gyy"]
+    Ta = scipy.linalg.cho_solve(scipy.linalg.cho_factor(inner_rec, lower=True), G["GYy"].T).T      # GYy inner_rec^-1
+    V = scipy.linalg.cho_solve(scipy.linalg.cho_factor(inner, lower=True), (Ta @ cross).T).T      # ... cross inner^-1
+    Wphi = scipy.linalg.cho_solve(scipy.linalg.cho_factor(Kmm, lower=True), (V[:, :m] @ Kzz).T).T
+    return np.hstack((Wphi, V[:, m:]))
 
 
 def dlqr(A, B, Q, R):

@@ -1,0 +1,163 @@
+"""GPU: ORACLE parity at the shapes bench.py times (BASELINE.json configs[3] and [4]) -- reference regressors.py:141-167.
+
+The benchmarked instantiation of the fused lift+Gram kernel is `gram_kernel<false>` (two chunk buffers, deferred completion
+signal), selected when the work plan keeps two chunks in flight (`nk_gram_plan` summary: nslots == 2; nk_gram.cu launch_gram).  Every case
+below asserts that plan first, so the test cannot silently move to the small-problem instantiation, and then feeds ONE numpy
+prefix (oracle/nk_oracle.py::synthetic) to both sides:
+
+  * seven Grams element-wise (relative Frobenius) <= 1e-12 against `O.grams` (scipy cdist + dgemm, the reference's calls);
+  * A / B / C / weights <= 1e-9 against `O.solve_abc(solver="chol")` where cond(inner_term) < 1e7 (gamma = 1e-3 at m = 4096);
+    at the bench's own gamma = 1e-4 (cond 5e7) the gate is max(1e-9, 3 x the oracle's own floor), the floor being how far the
+    oracle moves when its Grams are summed in a different chunk order (SURVEY 8c protocol);
+  * lift / predict <= 1e-9;
+  * ragged landmark counts that still select gram_kernel<false> (m = 1100, 2049; n not a multiple of the 512-sample chunk);
+  * m = 8192 (config 5): Grams and the batched `nk_cv_weights` against the oracle.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nk_oracle as O
+
+pytestmark = pytest.mark.gpu
+THREADS = os.cpu_count() or 1
+GRAMS = ("Gxx", "Gyx", "Gyy", "Gxu", "Gyu", "Guu", "GYy")
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def plan_summary(m, d, p, chunk, sms):
+    from nys_koop_lqr_b200 import _lib
+    summ = (C.c_int * 12)()
+    assert _lib.load().nk_gram_plan(m, d, p, chunk, sms, summ, None, 0) > 0
+    keys = ("chunk", "MP", "KLS", "EP", "psi_rows", "nblk", "ntiles", "n_pk", "n_lf", "n_sy", "period_len", "nslots")
+    return dict(zip(keys, summ))
+
+
+def assert_headline_instantiation(engine, m, d, p, chunk=0):
+    s = plan_summary(m, d, p, chunk, engine.sm_count())
+    assert s["nslots"] == 2, f"plan {s} would run gram_kernel<true>, not the benched kernel (launch_gram: nslots > 2)"
+    return s
+
+
+def problem(n, d, p, m, seed):
+    Xs, U, Y = O.synthetic(n, d, p, seed=seed)
+    np.random.seed(seed)
+    Z = O.draw_landmarks(Y, m)                       # regressors.py:129-132
+    return Xs, U, Y, Z
+
+
+@pytest.fixture(scope="module")
+def headline(engine):
+    """n = 20 000 prefix at (m, d, p) = (4096, 192, 6), RBF l = 10: oracle Grams (two chunk orders) and GPU Grams."""
+    n, d, p, m = 20000, 192, 6, 4096
+    assert_headline_instantiation(engine, m, d, p)
+    Xs, U, Y, Z = problem(n, d, p, m, seed=11)
+    ls = np.full(d, 10.0)
+    ref = O.grams(Xs, Y, U, Z, O.RBF, ls, chunk=8192, threads=THREADS)
+    ref2 = O.grams(Xs, Y, U, Z, O.RBF, ls, chunk=1000, threads=THREADS)      # same sums, different order: the oracle's floor
+    Xa, Yd, Zd, il = dev(np.hstack((Xs, U))), dev(Y), dev(Z), dev(1.0 / ls)
+    G = engine.grams(Xa, Yd, Zd, il, O.RBF, p)
+    Kzz_ref = O.kernel_matrix(Z, Z, O.RBF, ls)
+    return dict(n=n, d=d, p=p, m=m, Xs=Xs, U=U, Y=Y, Z=Z, ls=ls, ref=ref, ref2=ref2, G=G, Zd=Zd, il=il, Kzz_ref=Kzz_ref)
+
+
+def test_grams_at_headline_shape(engine, headline):
+    h = headline
+    for k in GRAMS:
+        err = O.relerr(host(h["G"][k]), h["ref"][k])
+        assert err <= 1e-12, f"{k}: {err:.3e}"
+    assert torch.equal(h["G"]["Gxx"], h["G"]["Gxx"].T) and torch.equal(h["G"]["Gyy"], h["G"]["Gyy"].T)
+    # same launch again: bit-identical (fixed per-tile chunk order in the deferred-signal instantiation too)
+    G2 = engine.grams(dev(np.hstack((h["Xs"], h["U"]))), dev(h["Y"]), h["Zd"], h["il"], O.RBF, h["p"])
+    assert torch.equal(G2["_flat"], h["G"]["_flat"])
+
+
+@pytest.mark.parametrize("gamma", [1e-3, 1e-4])
+def test_abc_at_headline_shape(engine, headline, gamma):
+    h = headline
+    n, m, p = h["n"], h["m"], h["p"]
+    want = O.solve_abc(h["ref"], h["Kzz_ref"], gamma * n, solver="chol")
+    floor = max(O.relerr(a, b) for a, b in zip(O.solve_abc(h["ref2"], h["Kzz_ref"], gamma * n, solver="chol"), want))
+    Kzz = engine.kzz(h["Zd"], h["il"], O.RBF)
+    assert O.relerr(host(Kzz), h["Kzz_ref"]) <= 1e-13
+    Kmm = Kzz.clone(); Kmm.diagonal().add_(1e-6)
+    S, Sinv = engine.sym_sqrt(Kmm)
+    A, B, Cm, W = engine.solve_abc(h["G"], Kzz, S, Sinv, gamma * n)
+    errs = {k: O.relerr(host(g), w) for k, g, w in zip("ABCW", (A, B, Cm, W), want)}
+    gate = 1e-9 if gamma >= 1e-3 else max(1e-9, 3.0 * floor)
+    print(f"gamma={gamma:g}: GPU vs oracle {errs}, oracle floor under a chunk-order change {floor:.2e}, gate {gate:.2e}")
+    assert max(errs.values()) <= gate, (errs, floor)
+    if gamma >= 1e-3:
+        # lift and predict with the same landmark matrices (regressors.py:171-178, 48-55)
+        pts = h["Xs"][:300]
+        phi = engine.lift(h["Zd"], h["il"], O.RBF, Sinv, dev(pts))
+        w_, V = np.linalg.eigh(h["Kzz_ref"] + 1e-6 * np.eye(m))
+        Sinv_ref = (V / np.sqrt(w_)) @ V.T
+        phi_ref = Sinv_ref @ O.kernel_matrix(h["Z"], pts, O.RBF, h["ls"])
+        assert O.relerr(host(phi), phi_ref) <= 1e-9
+        Xa = np.hstack((pts, h["U"][:300]))
+        yh = engine.predict(h["Zd"], h["il"], O.RBF, Sinv, W, dev(Xa), p)
+        assert O.relerr(host(yh), (want[3] @ np.vstack((phi_ref, h["U"][:300].T))).T) <= 1e-9
+
+
+@pytest.mark.parametrize("n,d,p,m,kind,ls", [
+    (3001, 192, 6, 1100, O.RBF, 10.0),          # 9 landmark blocks, last one ragged; 6 chunks, last chunk ragged
+    (2500, 33, 3, 2049, O.MATERN52, 4.0),       # one landmark past a block edge; Matern; narrow state
+    (1537, 192, 6, 4096, O.RBF, 10.0),          # headline m with a 1-sample last chunk
+])
+def test_ragged_shapes_on_the_benched_instantiation(engine, n, d, p, m, kind, ls):
+    assert_headline_instantiation(engine, m, d, p)
+    Xs, U, Y, Z = problem(max(n, m), d, p, m, seed=n)
+    Xs, U, Y = Xs[:n], U[:n], Y[:n]
+    lsv = np.full(d, ls)
+    ref = O.grams(Xs, Y, U, Z, kind, lsv, threads=THREADS)
+    G = engine.grams(dev(np.hstack((Xs, U))), dev(Y), dev(Z), dev(1.0 / lsv), kind, p)
+    for k in GRAMS:
+        assert O.relerr(host(G[k]), ref[k]) <= 1e-12, k
+    # streamed in three uneven blocks == one shot (what the e2e path of bench.py does), to summation-order rounding
+    Xa, Yd = dev(np.hstack((Xs, U))), dev(Y)
+    engine.gram_begin(dev(Z), dev(1.0 / lsv), kind, p)
+    for s, e in ((0, 700), (700, 701), (701, n)):
+        engine.gram_update(Xa[s:e], Yd[s:e])
+    Gs = engine.gram_finalize()
+    for k in GRAMS:
+        assert O.relerr(host(Gs[k]), ref[k]) <= 1e-12, k
+
+
+def test_config5_shape_grams_and_cv_weights(engine):
+    """m = 8192 (BASELINE.json configs[4]): fused-kernel Grams and the batched prediction weights of two gammas."""
+    n, d, p, m = 9000, 192, 6, 8192
+    assert_headline_instantiation(engine, m, d, p)
+    Xs, U, Y, Z = problem(n, d, p, m, seed=5)
+    ls = np.full(d, 10.0)
+    ref = O.grams(Xs, Y, U, Z, O.RBF, ls, chunk=4500, threads=THREADS)
+    Zd, il = dev(Z), dev(1.0 / ls)
+    G = engine.grams(dev(np.hstack((Xs, U))), dev(Y), Zd, il, O.RBF, p)
+    for k in GRAMS:
+        assert O.relerr(host(G[k]), ref[k]) <= 1e-12, k
+    Kzz_ref = O.kernel_matrix(Z, Z, O.RBF, ls)
+    Kzz = engine.kzz(Zd, il, O.RBF)
+    assert O.relerr(host(Kzz), Kzz_ref) <= 1e-13
+    gammas = [1e-2, 1e-3]
+    Wk, info = engine.cv_weights(G, Kzz, [g * n for g in gammas])
+    assert info == [0, 0]
+    pts = np.hstack((Xs[:200], U[:200]))
+    feats = np.vstack((O.kernel_matrix(Z, Xs[:200], O.RBF, ls), U[:200].T))
+    for b, g in enumerate(gammas):
+        want = O.cv_weights(ref, Kzz_ref, g * n)
+        got = host(Wk[b])
+        # the weights themselves sit on the cond(K_mm) * eps floor (K_mm^-1 is applied last); what CV scoring consumes is the
+        # prediction Wk [k(Z,x); u] -- gate both
+        assert O.relerr(got @ feats, want @ feats) <= 1e-9, (g, O.relerr(got @ feats, want @ feats))
+        assert O.relerr(got, want) <= 1e-7, (g, O.relerr(got, want))
+    engine.release_scratch()
