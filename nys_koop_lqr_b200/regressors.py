@@ -10,9 +10,8 @@ methods raise.  The landmark draw stays the reference's own ``np.random.choice``
 """
 from __future__ import annotations
 
-import importlib.util
 import os
-import pathlib
+import zlib
 
 import numpy as np
 import scipy
@@ -645,36 +644,23 @@ KoopmanNystromRegressor.closed_loop = _closed_loop
 
 
 # ----------------------------------------------------------------------------------------------
-# out-of-scope baselines (regressors.py:58-111 exact-kernel, :181-234 thin-plate splines): not part of the B200
-# hot path.  They are re-exported from an upstream checkout only when NK_REFERENCE_PATH names one (so
-# that the scripts' spline comparisons keep working); otherwise instantiating them explains what to do.
+# comparator baselines (regressors.py:58-111 exact-kernel, :181-234 thin-plate splines): CPU classes, outside the B200 hot
+# path -- the scripts' 'splines' / exact-kernel branches instantiate them, so the drop-in module provides them
 # ----------------------------------------------------------------------------------------------
-def _load_upstream():
-    root = os.environ.get("NK_REFERENCE_PATH")       # opt-in only: the product never looks for a reference tree on its own
-    if not root:
-        return None
-    f = pathlib.Path(root) / "regressors.py"
-    if not f.exists():
-        return None
-    spec = importlib.util.spec_from_file_location("_nk_upstream_regressors", f)
-    mod = importlib.util.module_from_spec(spec)
-    try:
-        spec.loader.exec_module(mod)
-    except Exception:
-        return None
-    return mod
+from .baselines import _KernelFitMixin, _SplineFitMixin  # noqa: E402
 
 
-def _missing(name):
-    class _Missing(KoopmanRegressor):
-        def __init__(self, *a, **k):
-            raise NotImplementedError(
-                f"{name} is a CPU baseline outside the B200 hot path; point NK_REFERENCE_PATH at an upstream checkout "
-                "of LCSL/nys-koop-lqr to use the original class")
-    _Missing.__name__ = name
-    return _Missing
+class KoopmanKernelRegressor(_KernelFitMixin, KoopmanRegressor):
+    """Exact (n x n) kernel estimator, reference regressors.py:58-111 (CPU comparator)."""
+
+    def __init__(self, n_inputs, kernel=None, gamma=None):
+        KoopmanRegressor.__init__(self, n_inputs, gamma)
+        self._init_kernel_state(kernel)
 
 
-_up = _load_upstream()
-KoopmanKernelRegressor = getattr(_up, "KoopmanKernelRegressor", None) or _missing("KoopmanKernelRegressor")
-KoopmanSplineRegressor = getattr(_up, "KoopmanSplineRegressor", None) or _missing("KoopmanSplineRegressor")
+class KoopmanSplineRegressor(_SplineFitMixin, KoopmanRegressor):
+    """Thin-plate-spline EDMD (Korda & Mezic), reference regressors.py:181-234 (CPU comparator)."""
+
+    def __init__(self, n_inputs, state_bounds_params=None, m=None, gamma=None):
+        KoopmanRegressor.__init__(self, n_inputs, gamma, m)
+        self._init_spline_state(state_bounds_params)

@@ -128,9 +128,23 @@ def test_c_abi_fails_loudly_without_device():
     assert b"no CUDA device" in lib.nk_last_error_string(None) or b"CUDA" in lib.nk_last_error_string(None)
 
 
-def test_out_of_scope_baselines_are_importable():
+def test_comparator_baselines_work_on_the_host():
+    """The scripts' spline / exact-kernel branches (benchmark_lqr_classic.py:55,237,276; _cloth.py:44,199,232) instantiate these
+    CPU comparators from the drop-in module: same ctor parameters (sklearn clone), fit -> A, B, C, weights, predict."""
     import regressors as R
-    assert isinstance(R.KoopmanSplineRegressor, type) and isinstance(R.KoopmanKernelRegressor, type)
+    from sklearn.base import clone
+    rng = np.random.default_rng(0)
+    n, d, p = 90, 2, 1
+    X, Y = rng.standard_normal((n, d + p)), rng.standard_normal((n, d))
+    np.random.seed(1)
+    sp = clone(R.KoopmanSplineRegressor(p, state_bounds_params=np.array([1.5, 2.0]), m=12, gamma=1e-4))
+    sp.fit(X, Y)
+    assert sp.A.shape == (12, 12) and sp.B.shape == (12, p) and sp.C.shape == (d, 12) and sp.predict(X[:5]).shape == (5, d)
+    assert np.allclose(sp.predict(X[:5]), (sp.weights @ np.vstack((sp.lift(X[:5, :d].T), X[:5, d:].T))).T)
+    ke = clone(R.KoopmanKernelRegressor(p, kernel=R.KernelWrapper([1.0, 1.0]), gamma=1e-3))
+    ke.fit(X, Y)
+    assert ke.A.shape == (n, n) and ke.B.shape == (n, p) and ke.C.shape == (d, n) and ke.lift(X[:3, :d].T).shape == (n, 3)
+    assert np.isfinite(ke.predict(X)).all() and ke.predict(X).shape == (n, d)
 
 
 def test_header_is_plain_c_and_links_from_c(tmp_path):

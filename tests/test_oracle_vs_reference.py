@@ -141,3 +141,29 @@ def test_golden_G3_G4_cloth_pickles_and_gains():
     assert np.array_equal(Z.T, reg.nystrom_centers_output)
     fit = O.fit(X, Y, 6, O.RBF, np.full(192, 10.0), 1e-7, Z=Z, solver="reference")
     assert O.relerr(fit["A"], A) <= 5e-3 and O.relerr(fit["B"], B) <= 5e-4 and O.relerr(fit["C"], C) <= 5e-3
+
+
+@pytest.mark.needs_reference
+def test_comparator_baselines_match_the_reference_classes():
+    """nys_koop_lqr_b200/baselines.py (CPU comparators exported by the drop-in module) against regressors.py:58-111, 181-234."""
+    import importlib.util
+    import regressors as R
+    spec = importlib.util.spec_from_file_location("_ref_regressors_baselines", REF / "regressors.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    rng = np.random.default_rng(5)
+    n, d, p = 150, 2, 1
+    X, Y = rng.standard_normal((n, d + p)), rng.standard_normal((n, d))
+    a = R.KoopmanKernelRegressor(p, kernel=R.KernelWrapper([1.0, 1.5]), gamma=1e-3)
+    b = ref.KoopmanKernelRegressor(p, kernel=ref.KernelWrapper([1.0, 1.5]), gamma=1e-3)
+    a.fit(X, Y); b.fit(X, Y)
+    for k in ("A", "B", "C", "weights"):
+        assert O.relerr(getattr(a, k), getattr(b, k)) <= 1e-12, k
+    assert O.relerr(a.lift(X[:9, :d].T), b.lift(X[:9, :d].T)) <= 1e-12
+    for bounds in (None, np.array([1.5, 2.0])):
+        np.random.seed(3); a = R.KoopmanSplineRegressor(p, state_bounds_params=bounds, m=15, gamma=1e-4); a.fit(X, Y)
+        with np.errstate(all="ignore"):
+            np.random.seed(3); b = ref.KoopmanSplineRegressor(p, state_bounds_params=bounds, m=15, gamma=1e-4); b.fit(X, Y)
+        for k in ("A", "B", "C", "weights", "centers"):
+            assert O.relerr(getattr(a, k), getattr(b, k)) <= 1e-12, k
+        assert O.relerr(a.predict(X[:7]), b.predict(X[:7])) <= 1e-12
