@@ -135,6 +135,9 @@ def cpu_rate(n_sample, m, d, p, seed=0):
 
 
 def unmodified_reference_fit(d, p, m_ref=1024, sizes=(4000, 20000)):
+    m_ref = int(os.environ.get("NK_BENCH_REF_M", m_ref))                      # tests shrink it
+    if os.environ.get("NK_BENCH_REF_N"):
+        sizes = tuple(int(v) for v in os.environ["NK_BENCH_REF_N"].split(","))
     """SURVEY 8(d): the UNMODIFIED reference (baseline/_ref/regressors.py, installed from /root/reference by
     tools/stage_reference.sh) timed on the host: KoopmanNystromRegressor.fit at n in `sizes`, fitted to T(n) = T0 + n / r.
     m = 4096 costs ~420 s per fit (two scipy sqrtm of 138 s each, SURVEY 3.1), so the in-bench fit runs at m_ref landmarks and the
@@ -178,7 +181,7 @@ def run_reference_arm(args):
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = n_sample / (ms * 1e-3)
-    unmod = None if args.no_ref_fit else unmodified_reference_fit(d, p)
+    unmod = None if args.no_ref_fit else unmodified_reference_fit(d, p)     # kind stays "port": the per-step value is the port's
     sample = (f"{n_sample} of the {args.n} samples per step, m={m}, d={d}: the n-proportional stage of the reference fit (cdist kernel lift "
               f"+ 7 Gram dgemms, regressors.py:141-164) restated in oracle/nk_oracle.py with the same scipy/numpy calls, cdist spread over "
               f"{os.cpu_count()} threads (the reference runs it on one).  The reference's n-independent stage (2 sqrtm + 2 lstsq + 2 solve, "
@@ -189,7 +192,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "_ref+port" if unmod else "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample,
                          "unmodified_reference": unmod},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

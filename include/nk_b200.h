@@ -45,11 +45,20 @@ int nk_release_scratch(nk_handle *h);
  * with Phi_x = k(Z, X_state) and Phi_y = k(Z, Y), both (m,n) and never materialised.  Any output may be NULL. */
 int nk_gram_begin(nk_handle *h, const double *Z, long long ldz, int m, int d, int p,
                   const double *inv_ls, int kind, int chunk, void *stream);
+/* Same with DISTINCT input landmarks (regressors.py:133-134: a caller may inject nystrom_centers_input != _output; both (m,d)):
+ * Phi_x = k(Z_in, X_state), Phi_y = k(Z_out, Y).  nk_gram_begin is this call with Z_in == Z_out. */
+int nk_gram_begin_io(nk_handle *h, const double *Z_in, long long ldz_in, const double *Z_out, long long ldz_out, int m, int d, int p,
+                     const double *inv_ls, int kind, int chunk, void *stream);
 int nk_gram_update(nk_handle *h, const double *X, long long ldx, const double *Y, long long ldy,
                    long long n, void *stream);
 int nk_gram_finalize(nk_handle *h, double *Gxx, long long ld_gxx, double *Gyx, long long ld_gyx,
                      double *Gyy, long long ld_gyy, double *Gxu, long long ld_gxu, double *Gyu, long long ld_gyu,
                      double *Guu, long long ld_guu, double *GYy, long long ld_gYy, int accumulate, void *stream);
+/* The fused kernel has no grid-wide barrier: items wait on counters.  Every such wait carries a watchdog (20 s); if it fires the
+ * kernel drains and the accumulation is abandoned.  nk_gram_finalize latches the flag (stream-ordered, no wait); it is reported as
+ * NK_E_STATE by the next SYNCHRONISING call (nk_solve_abc / nk_solve_abc_part / nk_cv_weights) or by nk_gram_status, which
+ * synchronises `stream` and returns NK_OK / NK_E_STATE. */
+int nk_gram_status(nk_handle *h, void *stream);
 /* Introspection, HOST ONLY (no device needed): the work plan nk_gram_begin builds for these sizes on a GPU with sm_count SMs.
  * summary[12] = {chunk, MP, KLS, EP, psi_rows, nblk, ntiles, n_pack, n_lift, n_gram, period_len, nslots};  items (may be NULL)
  * receives up to items_cap entries of ONE period of the global work order, 4 ints each {type (0 pack, 1 lift, 2 Gram tile), a, b, c}
@@ -94,15 +103,43 @@ int nk_sym_sqrt(nk_handle *h, int n, const double *K, long long ldk, double lamb
                 double *S, long long lds, double *Sinv, long long ldsi, int *iters, void *stream);
 
 /* ---- Grams -> Koopman matrices  (regressors.py:147-169) ----
- * inner = [[Gxx + gn*Kmm, Gxu],[Gxu^T, Guu + gn*I]],  G = S^-1 [Gyx|Gyu] inner^-1 blkdiag(Kzz S^-1, I_p)
- * A = G[:, :m], B = G[:, m:];  C = GYy (gn*Kmm + Gyy)^-1 S;  W = C G;  Kmm = Kzz + jitter*I.
- * Outputs: A (m,m), B (m,p), C (d,m), W (d,m+p).  info (host): 0, or 1/2 if the first/second system is not SPD.
- * The call synchronises the stream twice to read the two Cholesky verdicts; when it returns NK_OK, A and B are COMPLETE on
- * the device (a caller may start downloading them on another stream), C and W complete in stream order. */
-int nk_solve_abc(nk_handle *h, int m, int p, int d, double gamma_n, double jitter,
-                 const double *Gxx, const double *Gyx, const double *Gyy, const double *Gxu, const double *Gyu,
-                 const double *Guu, const double *GYy, const double *Kzz, const double *S, const double *Sinv,
-                 double *A, double *B, double *C, double *W, int *info, void *stream);
+ * The seven data-sample Grams (outputs of nk_gram_finalize, possibly summed over devices) and the landmark-only matrices travel
+ * as two plain structs of caller-owned device pointers, each row-major with its own leading dimension (elements). */
+typedef struct nk_grams {
+    const double *Gxx; long long ld_gxx;   /* (m,m) Phi_x Phi_x^T */
+    const double *Gyx; long long ld_gyx;   /* (m,m) Phi_y Phi_x^T */
+    const double *Gyy; long long ld_gyy;   /* (m,m) Phi_y Phi_y^T */
+    const double *Gxu; long long ld_gxu;   /* (m,p) Phi_x U   (NULL when p == 0) */
+    const double *Gyu; long long ld_gyu;   /* (m,p) Phi_y U */
+    const double *Guu; long long ld_guu;   /* (p,p) U^T U */
+    const double *GYy; long long ld_gYy;   /* (d,m) Y^T Phi_y^T */
+} nk_grams;
+typedef struct nk_landmarks {
+    const double *Kzz; long long ld_kzz;       /* (m,m) k(Z_out, Z_out), no jitter (regressors.py:144) */
+    const double *S; long long ld_s;           /* (m,m) (Kzz + jitter I)^(1/2), symmetric (regressors.py:140) */
+    const double *Sinv; long long ld_sinv;     /* (m,m) its inverse */
+    const double *Kzz_in; long long ld_kzz_in; /* (m,m) k(Z_in, Z_in) -- NULL when the input landmarks ARE the output landmarks */
+    const double *Kio; long long ld_kio;       /* (m,m) k(Z_in, Z_out) (regressors.py:144) -- NULL together with Kzz_in */
+} nk_landmarks;
+/* inner = [[Gxx + gn*(Kzz_in + jitter I), Gxu],[Gxu^T, Guu + gn*I]],  G = S^-1 [Gyx|Gyu] inner^-1 blkdiag(Kio S^-1, I_p)
+ * A = G[:, :m], B = G[:, m:];  C = GYy (gn*(Kzz + jitter I) + Gyy)^-1 S;  W = C G.   (Kzz_in = Kio = Kzz when NULL; then
+ * Kzz S^-1 = S - jitter S^-1 is formed elementwise.)  Cholesky takes the place of scipy.linalg.lstsq (same solve while nothing
+ * is truncated); info (host int*, may be NULL): 0, or 1 / 2 if inner_term / inner_term_rec is not positive definite.
+ * Outputs: A (m,m), B (m,p), C (d,m), W (d,m+p), each with a leading dimension.  ONE stream synchronisation (the verdicts).
+ *
+ * nk_solve_abc_part computes a slice of the same solve, for sharding it over devices (each right-hand-side column is
+ * independent): rows [g_row0, g_row0+g_rows) of G^T ((m+p) x m: row c = column c of [A|B]) and rows [c_row0, c_row0+c_rows) of
+ * C^T (m x d).  Either range may be empty.  Every device factors both systems, solves only its columns; the slices are
+ * exchanged by the caller (one all-gather each) and nk_solve_abc_finish turns the assembled G^T, C^T into A, B, C, W = C G
+ * (any output may be NULL; W needs C).  nk_solve_abc is part(all rows) + finish on one device. */
+int nk_solve_abc(nk_handle *h, int m, int p, int d, double gamma_n, double jitter, const nk_grams *G, const nk_landmarks *L,
+                 double *A, long long lda, double *B, long long ldb, double *C, long long ldc, double *W, long long ldw, int *info,
+                 void *stream);
+int nk_solve_abc_part(nk_handle *h, int m, int p, int d, double gamma_n, double jitter, const nk_grams *G, const nk_landmarks *L,
+                      int g_row0, int g_rows, double *GT, long long ld_gt, int c_row0, int c_rows, double *CT, long long ld_ct,
+                      int *info, void *stream);
+int nk_solve_abc_finish(nk_handle *h, int m, int p, int d, const double *GT, long long ld_gt, const double *CT, long long ld_ct,
+                        double *A, long long lda, double *B, long long ldb, double *C, long long ldc, double *W, long long ldw, void *stream);
 
 /* ---- lift  phi = S^-1 k(Z, X)  (regressors.py:171-178): X (N,d) rows -> Phi (m,N); PhiT (N,m) is the same data
  * transposed (either output may be NULL).  N is limited by scratch memory (N*(m+d+2) doubles); callers chunk. ---- */
@@ -142,15 +179,14 @@ int nk_closed_loop(nk_handle *h, int m, int p, int d, int steps, long long nb, c
  *   Cholesky batched over the regularisation grid) and solved for the d rows scoring needs:
  *     Wk[b] (d, m+p) = [ V_phi Kzz Kmm^-1 | V_u ],  V = GYy (gn_b Kmm + Gyy)^-1 [Gyx|Gyu] inner_b^-1,
  *   so that regressors.py:48-55 reads  Yhat = Wk[b] [k(Z,x); u]   (= weights [S^-1 k(Z,x); u]; the S factors cancel).
- *   Wk: device (nlam, d, m+p).  info: HOST ints (nlam), 0 ok / 1 inner_term / 2 inner_term_rec / 3 K_mm not SPD.
+ *   Wk: device (nlam, d, ld_wk >= m+p).  info: HOST ints (nlam), 0 ok / 1 inner_term / 2 inner_term_rec / 3 K_mm not SPD.
  *   The call synchronises the stream.
  * nk_cv_score: sse[r] += sum_s (Yhat[s, r] - Y[s, r % d])^2 for the R = nlam*d stacked weight rows Wk (R, m+p) over
  *   the N held-out samples X_aug (N, d+p), Y (N, d).  sse (R) device, caller-zeroed (accumulates across calls).
  *   sklearn's 'neg_root_mean_squared_error' for value b is  -mean_j sqrt(sse[b*d + j] / N).
  * nk_axpy: y += alpha x (count doubles) -- combines per-fold Grams into training-fold Grams on the device. */
-int nk_cv_weights(nk_handle *h, int m, int p, int d, int nlam, const double *gamma_n, double jitter,
-                  const double *Gxx, const double *Gyx, const double *Gyy, const double *Gxu, const double *Gyu,
-                  const double *Guu, const double *GYy, const double *Kzz, double *Wk, int *info, void *stream);
+int nk_cv_weights(nk_handle *h, int m, int p, int d, int nlam, const double *gamma_n, double jitter, const nk_grams *G,
+                  const double *Kzz, long long ld_kzz, double *Wk, long long ld_wk, int *info, void *stream);
 int nk_cv_score(nk_handle *h, const double *Z, long long ldz, int m, int d, int p, const double *inv_ls, int kind,
                 const double *Wk, int R, const double *X_aug, long long ldx, const double *Y, long long ldy, long long N,
                 double *sse, void *stream);

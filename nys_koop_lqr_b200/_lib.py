@@ -18,6 +18,21 @@ _ll = C.c_longlong
 _i = C.c_int
 _d = C.c_double
 
+
+
+class NkGrams(C.Structure):
+    """struct nk_grams of include/nk_b200.h: the seven data-sample Grams, device pointers + leading dimensions."""
+    _fields_ = [(f, t) for name in ("Gxx", "Gyx", "Gyy", "Gxu", "Gyu", "Guu", "GYy") for f, t in ((name, C.c_void_p), ("ld_" + name[0].lower() + name[1:], C.c_longlong))]
+
+
+class NkLandmarks(C.Structure):
+    """struct nk_landmarks: K_zz, S, S^-1 of the output landmarks; optional k(Z_in,Z_in), k(Z_in,Z_out) for distinct input landmarks."""
+    _fields_ = [("Kzz", C.c_void_p), ("ld_kzz", C.c_longlong), ("S", C.c_void_p), ("ld_s", C.c_longlong), ("Sinv", C.c_void_p), ("ld_sinv", C.c_longlong),
+                ("Kzz_in", C.c_void_p), ("ld_kzz_in", C.c_longlong), ("Kio", C.c_void_p), ("ld_kio", C.c_longlong)]
+
+
+_pG, _pL = C.POINTER(NkGrams), C.POINTER(NkLandmarks)
+
 _SIGNATURES = {
     "nk_version": ([], _i),
     "nk_create": ([C.POINTER(C.c_void_p), _i], _i),
@@ -26,6 +41,8 @@ _SIGNATURES = {
     "nk_device_sm_count": ([C.c_void_p], _i),
     "nk_release_scratch": ([C.c_void_p], _i),
     "nk_gram_begin": ([C.c_void_p, _c_dp, _ll, _i, _i, _i, _c_dp, _i, _i, C.c_void_p], _i),
+    "nk_gram_begin_io": ([C.c_void_p, _c_dp, _ll, _c_dp, _ll, _i, _i, _i, _c_dp, _i, _i, C.c_void_p], _i),
+    "nk_gram_status": ([C.c_void_p, C.c_void_p], _i),
     "nk_gram_update": ([C.c_void_p, _c_dp, _ll, _c_dp, _ll, _ll, C.c_void_p], _i),
     "nk_gram_finalize": ([C.c_void_p] + [_c_dp, _ll] * 7 + [_i, C.c_void_p], _i),
     "nk_gram_plan": ([_i, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), _i], _i),
@@ -39,12 +56,14 @@ _SIGNATURES = {
     "nk_potrf": ([C.c_void_p, _i, _c_dp, _ll, C.POINTER(_i), C.c_void_p], _i),
     "nk_trsm_lower": ([C.c_void_p, _i, _i, _i, _c_dp, _ll, _c_dp, _ll, C.c_void_p], _i),
     "nk_sym_sqrt": ([C.c_void_p, _i, _c_dp, _ll, _d, _c_dp, _ll, _c_dp, _ll, C.POINTER(_i), C.c_void_p], _i),
-    "nk_solve_abc": ([C.c_void_p, _i, _i, _i, _d, _d] + [_c_dp] * 14 + [C.POINTER(_i), C.c_void_p], _i),
+    "nk_solve_abc": ([C.c_void_p, _i, _i, _i, _d, _d, _pG, _pL] + [_c_dp, _ll] * 4 + [C.POINTER(_i), C.c_void_p], _i),
+    "nk_solve_abc_part": ([C.c_void_p, _i, _i, _i, _d, _d, _pG, _pL, _i, _i, _c_dp, _ll, _i, _i, _c_dp, _ll, C.POINTER(_i), C.c_void_p], _i),
+    "nk_solve_abc_finish": ([C.c_void_p, _i, _i, _i, _c_dp, _ll, _c_dp, _ll] + [_c_dp, _ll] * 4 + [C.c_void_p], _i),
     "nk_lift": ([C.c_void_p, _c_dp, _ll, _i, _i, _c_dp, _i, _c_dp, _ll, _c_dp, _ll, _ll, _c_dp, _ll, _c_dp, _ll, C.c_void_p], _i),
     "nk_predict": ([C.c_void_p, _c_dp, _ll, _i, _i, _i, _c_dp, _i, _c_dp, _ll, _c_dp, _ll, _c_dp, _ll, _ll, _c_dp, _ll, C.c_void_p], _i),
     "nk_rollout": ([C.c_void_p, _i, _i, _i, _i, _ll] + [_c_dp] * 10 + [C.c_void_p], _i),
     "nk_closed_loop": ([C.c_void_p, _i, _i, _i, _i, _ll] + [_c_dp] * 9 + [C.c_void_p], _i),
-    "nk_cv_weights": ([C.c_void_p, _i, _i, _i, _i, C.POINTER(_d), _d] + [_c_dp] * 9 + [C.POINTER(_i), C.c_void_p], _i),
+    "nk_cv_weights": ([C.c_void_p, _i, _i, _i, _i, C.POINTER(_d), _d, _pG, _c_dp, _ll, _c_dp, _ll, C.POINTER(_i), C.c_void_p], _i),
     "nk_cv_score": ([C.c_void_p, _c_dp, _ll, _i, _i, _i, _c_dp, _i, _c_dp, _i, _c_dp, _ll, _c_dp, _ll, _ll, _c_dp, C.c_void_p], _i),
     "nk_axpy": ([C.c_void_p, _ll, _d, _c_dp, _c_dp, C.c_void_p], _i),
 }

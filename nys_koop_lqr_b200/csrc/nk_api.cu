@@ -17,6 +17,14 @@ int check_cuda(nk_handle *h, cudaError_t e, const char *what) {
     if (e == cudaSuccess) return NK_OK;
     return set_err(h, NK_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
+int gram_watchdog_verdict(nk_handle *h) {
+    if (h->gram_err_host && *h->gram_err_host != 0) {
+        *h->gram_err_host = 0;
+        h->gram_open = false;
+        return set_err(h, NK_E_STATE, "fused lift+Gram kernel: a dependence wait timed out (work-plan bug or a lost CTA); the accumulation was abandoned");
+    }
+    return NK_OK;
+}
 int ensure(nk_handle *h, nk_devbuf &b, size_t bytes) {
     if (bytes == 0) bytes = 8;
     if (b.bytes >= bytes) return NK_OK;
@@ -152,10 +160,11 @@ int nk_create(nk_handle **out, int device) {
 int nk_destroy(nk_handle *h) {
     if (!h) return NK_OK;
     DeviceScope scope(h->device);
-    nk_devbuf *bufs[] = {&h->zp, &h->inv_ls, &h->center, &h->gws, &h->items, &h->counters, &h->tile_of, &h->dinfo};
+    nk_devbuf *bufs[] = {&h->zp, &h->zp_in, &h->gram_err, &h->inv_ls, &h->center, &h->gws, &h->items, &h->counters, &h->tile_of, &h->dinfo};
     for (nk_devbuf *b : bufs) if (b->ptr) cudaFree(b->ptr);
     for (int s = 0; s < kMaxSlots; s++) for (nk_devbuf *b : {&h->xp[s], &h->yp[s], &h->psi[s]}) if (b->ptr) cudaFree(b->ptr);
     for (nk_devbuf &b : h->dense) if (b.ptr) cudaFree(b.ptr);
+    if (h->gram_err_host) cudaFreeHost(h->gram_err_host);
     delete h;
     return NK_OK;
 }
@@ -165,7 +174,7 @@ int nk_release_scratch(nk_handle *h) {
     h->gram_open = false;      // an accumulation in progress is discarded: nk_gram_update / _finalize need a new nk_gram_begin
     NK_ON_DEVICE(h);
     NK_CUDA(h, cudaDeviceSynchronize());
-    nk_devbuf *bufs[] = {&h->zp, &h->inv_ls, &h->center, &h->gws, &h->items, &h->counters, &h->tile_of, &h->dinfo};
+    nk_devbuf *bufs[] = {&h->zp, &h->zp_in, &h->gram_err, &h->inv_ls, &h->center, &h->gws, &h->items, &h->counters, &h->tile_of, &h->dinfo};
     for (nk_devbuf *b : bufs) if (b->ptr) { cudaFree(b->ptr); b->ptr = nullptr; b->bytes = 0; }
     for (int s = 0; s < kMaxSlots; s++)
         for (nk_devbuf *b : {&h->xp[s], &h->yp[s], &h->psi[s]}) if (b->ptr) { cudaFree(b->ptr); b->ptr = nullptr; b->bytes = 0; }
@@ -218,9 +227,14 @@ int nk_gram_plan(int m, int d, int p, int chunk, int sm_count, int *summary, int
 
 int nk_gram_begin(nk_handle *h, const double *Z, long long ldz, int m, int d, int p, const double *inv_ls, int kind,
                   int chunk, void *stream_) {
+    return nk_gram_begin_io(h, Z, ldz, Z, ldz, m, d, p, inv_ls, kind, chunk, stream_);
+}
+
+int nk_gram_begin_io(nk_handle *h, const double *Z_in, long long ldzi, const double *Z, long long ldz, int m, int d, int p,
+                     const double *inv_ls, int kind, int chunk, void *stream_) {
     if (!h) return NK_E_INVALID;
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!Z || !inv_ls || m < 1 || d < 1 || p < 0 || ldz < d) return set_err(h, NK_E_INVALID, "nk_gram_begin: bad argument");
+    if (!Z || !Z_in || !inv_ls || m < 1 || d < 1 || p < 0 || ldz < d || ldzi < d) return set_err(h, NK_E_INVALID, "nk_gram_begin: bad argument");
     if (kind != NK_KERNEL_RBF && kind != NK_KERNEL_MATERN52) return set_err(h, NK_E_INVALID, "nk_gram_begin: unsupported kernel kind");
     if (p > kTile) return set_err(h, NK_E_INVALID, "nk_gram_begin: more than 128 control inputs are not supported");
     NK_ON_DEVICE(h);
@@ -237,6 +251,8 @@ int nk_gram_begin(nk_handle *h, const double *Z, long long ldz, int m, int d, in
 
     int rc;
     if ((rc = ensure(h, h->zp, (size_t)h->MP * h->KLS * kSlabK * 8)) != NK_OK) return rc;
+    h->distinct_in = (Z_in != Z);
+    if (h->distinct_in && (rc = ensure(h, h->zp_in, (size_t)h->MP * h->KLS * kSlabK * 8)) != NK_OK) return rc;
     if ((rc = ensure(h, h->inv_ls, (size_t)d * 8)) != NK_OK) return rc;
     if ((rc = ensure(h, h->center, (size_t)d * 8)) != NK_OK) return rc;
     for (int s = 0; s < h->nslots; s++) {
@@ -245,6 +261,9 @@ int nk_gram_begin(nk_handle *h, const double *Z, long long ldz, int m, int d, in
         if ((rc = ensure(h, h->psi[s], (size_t)h->psi_rows * chunk * 8)) != NK_OK) return rc;
     }
     if ((rc = ensure(h, h->gws, (size_t)h->ntiles * kTile * kTile * 8)) != NK_OK) return rc;
+    if ((rc = ensure(h, h->gram_err, 16)) != NK_OK) return rc;
+    if (!h->gram_err_host) { NK_CUDA(h, cudaHostAlloc((void **)&h->gram_err_host, 16, cudaHostAllocDefault)); *h->gram_err_host = 0; }
+    NK_CUDA(h, cudaMemsetAsync(h->gram_err.ptr, 0, 16, stream));
     if ((rc = ensure(h, h->items, period.size() * sizeof(GramItem))) != NK_OK) return rc;
     if ((rc = ensure(h, h->counters, (size_t)(kCounterTileVer + h->ntiles) * sizeof(int))) != NK_OK) return rc;
     if ((rc = ensure(h, h->tile_of, h->h_tile_of.size() * sizeof(int))) != NK_OK) return rc;
@@ -256,6 +275,12 @@ int nk_gram_begin(nk_handle *h, const double *Z, long long ldz, int m, int d, in
     landmark_center(Z, ldz, m, d, (double *)h->center.ptr, stream);
     launch_pack_landmarks(Z, ldz, m, d, h->MP, h->KLS, (const double *)h->inv_ls.ptr, (const double *)h->center.ptr,
                           (double *)h->zp.ptr, stream);
+    // distinct input landmarks share the shift of the output landmarks (distances are shift invariant; one shift per product)
+    if (h->distinct_in) {
+        launch_pack_landmarks(Z_in, ldzi, m, d, h->MP, h->KLS, (const double *)h->inv_ls.ptr, (const double *)h->center.ptr,
+                              (double *)h->zp_in.ptr, stream);
+        h->launches++;
+    }
     NK_CUDA(h, cudaMemsetAsync(h->gws.ptr, 0, (size_t)h->ntiles * kTile * kTile * 8, stream));
     NK_CUDA(h, cudaGetLastError());
     h->launches += 2;
@@ -280,7 +305,7 @@ int nk_gram_update(nk_handle *h, const double *X, long long ldx, const double *Y
     P.d = h->d; P.p = h->p; P.m = h->m; P.kind = h->kind;
     P.MP = h->MP; P.KLS = h->KLS; P.nk = h->nk_chunk; P.n_chunks = (int)n_chunks;
     P.psi_rp = h->psi_rows / kPanel; P.e_row0 = 2 * h->MP; P.EP = h->EP;
-    P.ZP = (const double *)h->zp.ptr; P.inv_ls = (const double *)h->inv_ls.ptr; P.center = (const double *)h->center.ptr;
+    P.ZP = (const double *)h->zp.ptr; P.ZPx = h->distinct_in ? (const double *)h->zp_in.ptr : P.ZP; P.inv_ls = (const double *)h->inv_ls.ptr; P.center = (const double *)h->center.ptr;
     P.nslots = h->nslots;
     for (int s = 0; s < kMaxSlots; s++) {
         const int u = s < h->nslots ? s : 0;
@@ -290,6 +315,7 @@ int nk_gram_update(nk_handle *h, const double *X, long long ldx, const double *Y
     P.items = (const GramItem *)h->items.ptr;
     P.period_len = h->period_len; P.n_pk = h->n_pk; P.n_lf = h->n_lf; P.n_sy = h->n_sy;
     P.counters = (int *)h->counters.ptr;
+    P.err = (int *)h->gram_err.ptr;
 #ifdef NK_GRAM_TIMING
     { int trc = ensure(h, h->dense[15], (size_t)h->sm_count * kConsumerWarps * 16 * sizeof(long long)); if (trc != NK_OK) return trc; }
     P.timing = (long long *)h->dense[15].ptr;
@@ -333,8 +359,17 @@ int nk_gram_finalize(nk_handle *h, double *Gxx, long long ld_gxx, double *Gyx, l
     if (Gyu && p) { launch_unpack(G, tof, nb, MP, E0, m, p, Gyu, ld_gyu, accumulate, stream); h->launches++; }
     if (Guu && p) { launch_unpack(G, tof, nb, E0, E0, p, p, Guu, ld_guu, accumulate, stream); h->launches++; }
     if (GYy) { launch_unpack(G, tof, nb, E0 + p, MP, d, m, GYy, ld_gYy, accumulate, stream); h->launches++; }
+    // latch the watchdog flag for the next synchronising call (stream-ordered; nothing waits here)
+    NK_CUDA(h, cudaMemcpyAsync(h->gram_err_host, h->gram_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
     NK_CUDA(h, cudaGetLastError());
     return NK_OK;
+}
+
+int nk_gram_status(nk_handle *h, void *stream_) {
+    if (!h) return NK_E_INVALID;
+    NK_ON_DEVICE(h);
+    NK_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream_));
+    return gram_watchdog_verdict(h);
 }
 
 }  // extern "C"

@@ -27,30 +27,31 @@ __global__ void axpy_kernel(long long n, double alpha, const double *x, double *
 }
 
 // out(r,c) = Kzz(r,c) + jitter*[r==c]
-__global__ void assemble_kmm_kernel(int m, double jitter, const double *Kzz, double *out, long long ld) {
+__global__ void assemble_kmm_kernel(int m, double jitter, const double *Kzz, long long ldk, double *out, long long ld) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
-    if (c < m) out[(long long)r * ld + c] = Kzz[(long long)r * m + c] + (r == c ? jitter : 0.0);
+    if (c < m) out[(long long)r * ld + c] = Kzz[(long long)r * ldk + c] + (r == c ? jitter : 0.0);
 }
 // batched over blockIdx.z: rec_b = gn_b (Kzz + jitter I) + Gyy
-__global__ void assemble_rec_batched_kernel(int m, const double *gn, double jitter, const double *Gyy, const double *Kzz, double *out,
-                                            long long ld, long long stride) {
+__global__ void assemble_rec_batched_kernel(int m, const double *gn, double jitter, const double *Gyy, long long ldyy, const double *Kzz,
+                                            long long ldk, double *out, long long ld, long long stride) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
     if (c >= m) return;
     const double g = gn[blockIdx.z];
-    out[(long long)blockIdx.z * stride + (long long)r * ld + c] = g * (Kzz[(long long)r * m + c] + (r == c ? jitter : 0.0)) + Gyy[(long long)r * m + c];
+    out[(long long)blockIdx.z * stride + (long long)r * ld + c] = g * (Kzz[(long long)r * ldk + c] + (r == c ? jitter : 0.0)) + Gyy[(long long)r * ldyy + c];
 }
 // batched: inner_b = [[Gxx + gn_b Kmm, Gxu],[Gxu^T, Guu + gn_b I]]
-__global__ void assemble_inner_batched_kernel(int m, int p, const double *gn, double jitter, const double *Gxx, const double *Gxu,
-                                              const double *Guu, const double *Kzz, double *inner, long long ld, long long stride) {
+__global__ void assemble_inner_batched_kernel(int m, int p, const double *gn, double jitter, const double *Gxx, long long ldxx,
+                                              const double *Gxu, long long ldxu, const double *Guu, long long lduu, const double *Kzz,
+                                              long long ldk, double *inner, long long ld, long long stride) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
     const int N1 = m + p;
     if (c >= N1) return;
     const double g = gn[blockIdx.z];
     double v;
-    if (r < m && c < m) v = Gxx[(long long)r * m + c] + g * (Kzz[(long long)r * m + c] + (r == c ? jitter : 0.0));
-    else if (r < m) v = Gxu[(long long)r * p + (c - m)];
-    else if (c < m) v = Gxu[(long long)c * p + (r - m)];
-    else v = Guu[(long long)(r - m) * p + (c - m)] + (r == c ? g : 0.0);
+    if (r < m && c < m) v = Gxx[(long long)r * ldxx + c] + g * (Kzz[(long long)r * ldk + c] + (r == c ? jitter : 0.0));
+    else if (r < m) v = Gxu[(long long)r * ldxu + (c - m)];
+    else if (c < m) v = Gxu[(long long)c * ldxu + (r - m)];
+    else v = Guu[(long long)(r - m) * lduu + (c - m)] + (r == c ? g : 0.0);
     inner[(long long)blockIdx.z * stride + (long long)r * ld + c] = v;
 }
 // dst_b (rows, cols; ld, stride) = src (rows, cols; lds) for every b
@@ -119,13 +120,16 @@ int nk_axpy(nk_handle *h, long long count, double alpha, const double *x, double
     return NK_OK;
 }
 
-int nk_cv_weights(nk_handle *h, int m, int p, int d, int nlam, const double *gamma_n, double jitter, const double *Gxx,
-                  const double *Gyx, const double *Gyy, const double *Gxu, const double *Gyu, const double *Guu, const double *GYy,
-                  const double *Kzz, double *Wk, int *info, void *stream_) {
+int nk_cv_weights(nk_handle *h, int m, int p, int d, int nlam, const double *gamma_n, double jitter, const nk_grams *G,
+                  const double *Kzz, long long ld_kzz, double *Wk, long long ld_wk, int *info, void *stream_) {
     if (!h) return NK_E_INVALID;
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (m < 1 || p < 0 || d < 1 || nlam < 1 || nlam > 4096 || !gamma_n || !Gxx || !Gyx || !Gyy || !GYy || !Kzz || !Wk || (p && (!Gxu || !Gyu || !Guu)))
+    if (m < 1 || p < 0 || d < 1 || nlam < 1 || nlam > 4096 || !gamma_n || !G || !G->Gxx || !G->Gyx || !G->Gyy || !G->GYy || !Kzz || !Wk ||
+        (p && (!G->Gxu || !G->Gyu || !G->Guu)))
         return set_err(h, NK_E_INVALID, "nk_cv_weights: bad argument");
+    if (G->ld_gxx < m || G->ld_gyx < m || G->ld_gyy < m || G->ld_gYy < m || ld_kzz < m || ld_wk < m + p || (p && (G->ld_gxu < p || G->ld_gyu < p || G->ld_guu < p)))
+        return set_err(h, NK_E_INVALID, "nk_cv_weights: a leading dimension is smaller than the row length");
+    const double *Gxx = G->Gxx, *Gyx = G->Gyx, *Gyy = G->Gyy, *Gxu = G->Gxu, *Gyu = G->Gyu, *Guu = G->Guu, *GYy = G->GYy;
     NK_ON_DEVICE(h);
     int rc;
     const int N1 = m + p, ld1 = even_c(N1), ldm = even_c(m);
@@ -151,40 +155,42 @@ int nk_cv_weights(nk_handle *h, int m, int p, int d, int nlam, const double *gam
 
     const dim3 block(128);
     // (1) Kmm = Kzz + jitter I = Lk Lk^T (shared by the whole batch)
-    assemble_kmm_kernel<<<dim3((m + 127) / 128, m), block, 0, stream>>>(m, jitter, Kzz, Lk, ldm);
+    assemble_kmm_kernel<<<dim3((m + 127) / 128, m), block, 0, stream>>>(m, jitter, Kzz, ld_kzz, Lk, ldm);
     h->launches++;
     potrf_batched(h, 1, m, Lk, ldm, 0, Lkt, ldm, 0, dinvk, dinvkT, 0, dinfo + 2 * nlam, stream);
     // (2) cross^T = [Gyx | Gyu]^T  ((m+p) x m)
-    transpose(h, m, m, Gyx, m, crossT, ldm, stream);
-    if (p) transpose(h, m, p, Gyu, p, crossT + (long long)m * ldm, ldm, stream);
+    transpose(h, m, m, Gyx, G->ld_gyx, crossT, ldm, stream);
+    if (p) transpose(h, m, p, Gyu, G->ld_gyu, crossT + (long long)m * ldm, ldm, stream);
     // (3) reconstruction systems  rec_b = gn_b Kmm + Gyy  (regressors.py:162), factored as one batch
-    assemble_rec_batched_kernel<<<dim3((m + 127) / 128, m, nlam), block, 0, stream>>>(m, dgn, jitter, Gyy, Kzz, Lb, ldm, sM);
+    assemble_rec_batched_kernel<<<dim3((m + 127) / 128, m, nlam), block, 0, stream>>>(m, dgn, jitter, Gyy, G->ld_gyy, Kzz, ld_kzz, Lb, ldm, sM);
     h->launches++;
     potrf_batched(h, nlam, m, Lb, ldm, sM, Ltb, ldm, sM, dinv, dinvT, sD, dinfo, stream);
     // (4) Ta_b = GYy rec_b^-1   (d rows)
-    broadcast_rows_kernel<<<dim3((m + 127) / 128, d, nlam), block, 0, stream>>>(d, m, GYy, m, Ta, ldm, (long long)d * ldm);
+    broadcast_rows_kernel<<<dim3((m + 127) / 128, d, nlam), block, 0, stream>>>(d, m, GYy, G->ld_gYy, Ta, ldm, (long long)d * ldm);
     h->launches++;
     trsm_fwd_t_rl(h, nlam, m, d, Lb, ldm, sM, dinv, sD, Ta, ldm, (long long)d * ldm, stream);
     trsm_bwd_t_rl(h, nlam, m, d, Ltb, ldm, sM, dinvT, sD, Ta, ldm, (long long)d * ldm, stream);
     // (5) Tb_b = Ta_b [Gyx | Gyu]   (d x (m+p))
     gemm_nt_batched(h, nlam, d, N1, m, 1.0, Ta, ldm, (long long)d * ldm, crossT, ldm, 0, 0.0, Tb, ld1, (long long)d * ld1, 0.0, 0, nullptr, 0, 0, stream);
     // (6) dynamics systems inner_b (regressors.py:148,151), one batch;  V_b = Tb_b inner_b^-1
-    assemble_inner_batched_kernel<<<dim3((N1 + 127) / 128, N1, nlam), block, 0, stream>>>(m, p, dgn, jitter, Gxx, Gxu, Guu, Kzz, Lb, ld1, sM);
+    assemble_inner_batched_kernel<<<dim3((N1 + 127) / 128, N1, nlam), block, 0, stream>>>(m, p, dgn, jitter, Gxx, G->ld_gxx, Gxu, G->ld_gxu, Guu,
+                                                                                          G->ld_guu, Kzz, ld_kzz, Lb, ld1, sM);
     h->launches++;
     potrf_batched(h, nlam, N1, Lb, ld1, sM, Ltb, ld1, sM, dinv, dinvT, sD, dinfo + nlam, stream);
     trsm_fwd_t_rl(h, nlam, N1, d, Lb, ld1, sM, dinv, sD, Tb, ld1, (long long)d * ld1, stream);
     trsm_bwd_t_rl(h, nlam, N1, d, Ltb, ld1, sM, dinvT, sD, Tb, ld1, (long long)d * ld1, stream);
     // (7) Tc_b = V_phi,b Kzz Kmm^-1 : all nlam*d rows against the one factor of Kmm
-    gemm_nt_batched(h, nlam, d, m, m, 1.0, Tb, ld1, (long long)d * ld1, Kzz, m, 0, 0.0, Tc, ldm, (long long)d * ldm, 0.0, 0, nullptr, 0, 0, stream);
+    gemm_nt_batched(h, nlam, d, m, m, 1.0, Tb, ld1, (long long)d * ld1, Kzz, ld_kzz, 0, 0.0, Tc, ldm, (long long)d * ldm, 0.0, 0, nullptr, 0, 0, stream);
     trsm_fwd_t_rl(h, 1, m, nlam * d, Lk, ldm, 0, dinvk, 0, Tc, ldm, 0, stream);
     trsm_bwd_t_rl(h, 1, m, nlam * d, Lkt, ldm, 0, dinvkT, 0, Tc, ldm, 0, stream);
     // (8) Wk_b = [Tc_b | V_u,b]
-    NK_CUDA(h, cudaMemcpy2DAsync(Wk, (size_t)N1 * 8, Tc, (size_t)ldm * 8, (size_t)m * 8, (size_t)nlam * d, cudaMemcpyDeviceToDevice, stream));
-    if (p) NK_CUDA(h, cudaMemcpy2DAsync(Wk + m, (size_t)N1 * 8, Tb + m, (size_t)ld1 * 8, (size_t)p * 8, (size_t)nlam * d, cudaMemcpyDeviceToDevice, stream));
+    NK_CUDA(h, cudaMemcpy2DAsync(Wk, (size_t)ld_wk * 8, Tc, (size_t)ldm * 8, (size_t)m * 8, (size_t)nlam * d, cudaMemcpyDeviceToDevice, stream));
+    if (p) NK_CUDA(h, cudaMemcpy2DAsync(Wk + m, (size_t)ld_wk * 8, Tb + m, (size_t)ld1 * 8, (size_t)p * 8, (size_t)nlam * d, cudaMemcpyDeviceToDevice, stream));
     std::vector<int> hinfo(2 * nlam + 1, 0);
     NK_CUDA(h, cudaMemcpyAsync(hinfo.data(), dinfo, sizeof(int) * (2 * nlam + 1), cudaMemcpyDeviceToHost, stream));
     NK_CUDA(h, cudaStreamSynchronize(stream));
     NK_CUDA(h, cudaGetLastError());
+    if ((rc = gram_watchdog_verdict(h)) != NK_OK) return rc;
     int bad = 0;
     for (int b = 0; b < nlam; b++) {
         int v = 0;

@@ -761,91 +761,167 @@ int nk_sym_sqrt(nk_handle *h, int n, const double *K, long long ldk, double lamb
 }
 
 // ---- assemble kernels for the two regularised systems ----
-__global__ void assemble_inner_kernel(int m, int p, double gn, double jitter, const double *Gxx, const double *Gxu, const double *Guu,
-                                      const double *Kzz, double *inner, long long ld) {
+__global__ void assemble_inner_kernel(int m, int p, double gn, double jitter, const double *Gxx, long long ldxx, const double *Gxu,
+                                      long long ldxu, const double *Guu, long long lduu, const double *Kin, long long ldk, double *inner,
+                                      long long ld) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
     const int N1 = m + p;
     if (c >= N1) return;
     double v;
-    if (r < m && c < m) v = Gxx[(long long)r * m + c] + gn * (Kzz[(long long)r * m + c] + (r == c ? jitter : 0.0));
-    else if (r < m) v = Gxu[(long long)r * p + (c - m)];
-    else if (c < m) v = Gxu[(long long)c * p + (r - m)];
-    else v = Guu[(long long)(r - m) * p + (c - m)] + (r == c ? gn : 0.0);
+    if (r < m && c < m) v = Gxx[(long long)r * ldxx + c] + gn * (Kin[(long long)r * ldk + c] + (r == c ? jitter : 0.0));
+    else if (r < m) v = Gxu[(long long)r * ldxu + (c - m)];
+    else if (c < m) v = Gxu[(long long)c * ldxu + (r - m)];
+    else v = Guu[(long long)(r - m) * lduu + (c - m)] + (r == c ? gn : 0.0);
     inner[(long long)r * ld + c] = v;
 }
-__global__ void assemble_rec_kernel(int m, double gn, double jitter, const double *Gyy, const double *Kzz, double *out, long long ld) {
+__global__ void assemble_rec_kernel(int m, double gn, double jitter, const double *Gyy, long long ldyy, const double *Kzz, long long ldk,
+                                    double *out, long long ld) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
     if (c >= m) return;
-    out[(long long)r * ld + c] = gn * (Kzz[(long long)r * m + c] + (r == c ? jitter : 0.0)) + Gyy[(long long)r * m + c];
+    out[(long long)r * ld + c] = gn * (Kzz[(long long)r * ldk + c] + (r == c ? jitter : 0.0)) + Gyy[(long long)r * ldyy + c];
 }
-__global__ void set_identity_block_kernel(int p, double *M, long long ld) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < p) M[(long long)i * ld + i] = 1.0;
+// rows [row0, row0 + rows) of right^T = blkdiag(S^-1 Kzz, I_p) when the input landmarks are the output landmarks:
+// S^-1 Kzz = S^-1 (S^2 - jitter I) = S - jitter S^-1  (K_mm = Kzz + jitter I = S^2) -- elementwise, and more accurate than the product
+__global__ void right_rows_kernel(int m, int p, int row0, int rows, double jitter, const double *S, long long lds, const double *Sinv,
+                                  long long ldsi, double *Rt, long long ld) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, rr = blockIdx.y;
+    if (c >= m + p || rr >= rows) return;
+    const int r = row0 + rr;
+    double v = 0.0;
+    if (r < m && c < m) v = S[(long long)r * lds + c] - jitter * Sinv[(long long)r * ldsi + c];
+    else if (r >= m && c == r) v = 1.0;
+    Rt[(long long)rr * ld + c] = v;
+}
+// rows of right^T below / right of the landmark block when that block came from a product (distinct input landmarks)
+__global__ void right_pad_kernel(int m, int p, int row0, int rows, double *Rt, long long ld) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, rr = blockIdx.y;
+    if (c >= m + p || rr >= rows) return;
+    const int r = row0 + rr;
+    if (r < m && c < m) return;
+    Rt[(long long)rr * ld + c] = (r >= m && c == r) ? 1.0 : 0.0;
 }
 
-int nk_solve_abc(nk_handle *h, int m, int p, int d, double gamma_n, double jitter, const double *Gxx, const double *Gyx,
-                 const double *Gyy, const double *Gxu, const double *Gyu, const double *Guu, const double *GYy, const double *Kzz,
-                 const double *S, const double *Sinv, double *A, double *B, double *C, double *W, int *info, void *stream_) {
+static int check_solve_args(nk_handle *h, int m, int p, int d, const nk_grams *G, const nk_landmarks *L, const char *who) {
+    if (m < 1 || p < 0 || d < 1 || !G || !L || !G->Gxx || !G->Gyx || !G->Gyy || !G->GYy || !L->Kzz || !L->S || !L->Sinv ||
+        (p && (!G->Gxu || !G->Gyu || !G->Guu)) || ((L->Kzz_in == nullptr) != (L->Kio == nullptr)))
+        return set_err(h, NK_E_INVALID, std::string(who) + ": bad argument");
+    if (G->ld_gxx < m || G->ld_gyx < m || G->ld_gyy < m || G->ld_gYy < m || L->ld_kzz < m || L->ld_s < m || L->ld_sinv < m ||
+        (p && (G->ld_gxu < p || G->ld_gyu < p || G->ld_guu < p)) || (L->Kzz_in && (L->ld_kzz_in < m || L->ld_kio < m)))
+        return set_err(h, NK_E_INVALID, std::string(who) + ": a leading dimension is smaller than the row length");
+    return NK_OK;
+}
+
+int nk_solve_abc_part(nk_handle *h, int m, int p, int d, double gamma_n, double jitter, const nk_grams *G, const nk_landmarks *L,
+                      int g_row0, int g_rows, double *GT, long long ld_gt, int c_row0, int c_rows, double *CT, long long ld_ct,
+                      int *info, void *stream_) {
     if (!h) return NK_E_INVALID;
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (m < 1 || p < 0 || d < 1 || !Gxx || !Gyx || !Gyy || !GYy || !Kzz || !S || !Sinv || !A || !C || !W || (p && (!Gxu || !Gyu || !Guu || !B)))
-        return set_err(h, NK_E_INVALID, "nk_solve_abc: bad argument");
+    int rc = check_solve_args(h, m, p, d, G, L, "nk_solve_abc_part");
+    if (rc) return rc;
+    const int N1 = m + p;
+    if (g_row0 < 0 || g_rows < 0 || g_row0 + g_rows > N1 || c_row0 < 0 || c_rows < 0 || c_row0 + c_rows > m || (g_rows && (!GT || ld_gt < m)) ||
+        (c_rows && (!CT || ld_ct < d)))
+        return set_err(h, NK_E_INVALID, "nk_solve_abc_part: bad row range or output");
     NK_ON_DEVICE(h);
     if (info) *info = 0;
-    int rc;
-    const int N1 = m + p, ld1 = even(N1), ldm = even(m), nblk1 = (N1 + kDB - 1) / kDB;
+    const int ld1 = even(N1), ldm = even(m), nblk1 = (N1 + kDB - 1) / kDB;
     double *inner = dense_scratch(h, 0, (size_t)N1 * ld1, &rc); if (rc) return rc;
     double *Lt = dense_scratch(h, 1, (size_t)N1 * ld1, &rc); if (rc) return rc;
-    double *Rt = dense_scratch(h, 2, (size_t)N1 * ld1, &rc); if (rc) return rc;
-    double *crossT = dense_scratch(h, 3, (size_t)N1 * ldm, &rc); if (rc) return rc;
-    double *left = dense_scratch(h, 4, (size_t)m * ld1, &rc); if (rc) return rc;
-    double *Gm = dense_scratch(h, 5, (size_t)m * ld1, &rc); if (rc) return rc;
-    double *Gt = dense_scratch(h, 6, (size_t)N1 * ldm, &rc); if (rc) return rc;
+    double *Rt = dense_scratch(h, 2, (size_t)(g_rows > c_rows ? g_rows : c_rows) * ld1 + 2, &rc); if (rc) return rc;
+    double *cross = dense_scratch(h, 3, (size_t)m * ld1, &rc); if (rc) return rc;
+    double *T1 = dense_scratch(h, 4, (size_t)(g_rows > 0 ? g_rows : 1) * ldm, &rc); if (rc) return rc;
     double *dinv = dense_scratch(h, 8, (size_t)nblk1 * kDB * kDB, &rc); if (rc) return rc;
     double *dinvT = dense_scratch(h, 9, (size_t)nblk1 * kDB * kDB, &rc); if (rc) return rc;
     if ((rc = ensure(h, h->dinfo, 64)) != NK_OK) return rc;
-    int *dinfo = (int *)h->dinfo.ptr;
+    int *dinfo = (int *)h->dinfo.ptr;      // [0]: inner_term, [1]: inner_term_rec
     dim3 grid, block;
+    const bool same_landmarks = (L->Kzz_in == nullptr);
+    const double *Kin = same_landmarks ? L->Kzz : L->Kzz_in;
+    const long long ldkin = same_landmarks ? L->ld_kzz : L->ld_kzz_in;
+    NK_CUDA(h, cudaMemsetAsync(dinfo, 0, 2 * sizeof(int), stream));
 
-    // ---- dynamics: G = S^-1 [Gyx|Gyu] inner^-1 blkdiag(Kzz S^-1, I)   (regressors.py:147-159) ----
-    launch2d(N1, N1, grid, block);
-    assemble_inner_kernel<<<grid, block, 0, stream>>>(m, p, gamma_n, jitter, Gxx, Gxu, Guu, Kzz, inner, ld1);
-    h->launches++;
-    potrf_blocked(h, N1, inner, ld1, Lt, ld1, dinv, dinvT, dinfo, stream);
-    int hinfo = 0;
-    NK_CUDA(h, cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    NK_CUDA(h, cudaStreamSynchronize(stream));
-    if (hinfo != 0) { if (info) *info = 1; return set_err(h, NK_E_NOT_SPD, "nk_solve_abc: inner_term is not positive definite (pivot " + std::to_string(hinfo) + ")"); }
-    NK_CUDA(h, cudaMemsetAsync(Rt, 0, (size_t)N1 * ld1 * 8, stream));
-    gemm_nt(h, m, m, m, 1.0, Sinv, m, Kzz, m, 0.0, Rt, ld1, 0.0, 0, nullptr, 0, stream);       // right^T = blkdiag(S^-1 Kzz, I)
-    if (p) { set_identity_block_kernel<<<(p + 127) / 128, 128, 0, stream>>>(p, Rt + (long long)m * ld1 + m, ld1); h->launches++; }
-    trsm_fwd_t(h, N1, N1, inner, ld1, dinv, Rt, ld1, stream);                                   // sol^T = right^T inner^-1
-    trsm_bwd_t(h, N1, N1, Lt, ld1, dinvT, Rt, ld1, stream);
-    transpose(h, m, m, Gyx, m, crossT, ldm, stream);                                            // cross^T = [Gyx | Gyu]^T
-    if (p) transpose(h, m, p, Gyu, p, crossT + (long long)m * ldm, ldm, stream);
-    gemm_nt(h, m, N1, m, 1.0, Sinv, m, crossT, ldm, 0.0, left, ld1, 0.0, 0, nullptr, 0, stream);   // left = S^-1 cross
-    gemm_nt(h, m, N1, N1, 1.0, left, ld1, Rt, ld1, 0.0, Gm, ld1, 0.0, kGemmStoreT, Gt, ldm, stream);   // G = left sol
-    NK_CUDA(h, cudaMemcpy2DAsync(A, (size_t)m * 8, Gm, (size_t)ld1 * 8, (size_t)m * 8, m, cudaMemcpyDeviceToDevice, stream));
-    if (p) NK_CUDA(h, cudaMemcpy2DAsync(B, (size_t)p * 8, Gm + m, (size_t)ld1 * 8, (size_t)p * 8, m, cudaMemcpyDeviceToDevice, stream));
+    // ---- dynamics: G = S^-1 [Gyx|Gyu] inner^-1 blkdiag(K_io S^-1, I)   (regressors.py:147-159), rows of G^T = columns of G ----
+    if (g_rows > 0) {
+        launch2d(N1, N1, grid, block);
+        assemble_inner_kernel<<<grid, block, 0, stream>>>(m, p, gamma_n, jitter, G->Gxx, G->ld_gxx, G->Gxu, G->ld_gxu, G->Guu, G->ld_guu, Kin,
+                                                          ldkin, inner, ld1);
+        h->launches++;
+        potrf_blocked(h, N1, inner, ld1, Lt, ld1, dinv, dinvT, dinfo, stream);
+        // rows of right^T = blkdiag(S^-1 K_io^T, I)
+        launch2d(g_rows, N1, grid, block);
+        if (same_landmarks) {
+            right_rows_kernel<<<grid, block, 0, stream>>>(m, p, g_row0, g_rows, jitter, L->S, L->ld_s, L->Sinv, L->ld_sinv, Rt, ld1);
+        } else {
+            const int lm_rows = (g_row0 < m) ? ((g_row0 + g_rows < m ? g_row0 + g_rows : m) - g_row0) : 0;
+            if (lm_rows > 0)
+                gemm_nt(h, lm_rows, m, m, 1.0, L->Sinv + (long long)g_row0 * L->ld_sinv, L->ld_sinv, L->Kio, L->ld_kio, 0.0, Rt, ld1, 0.0, 0, nullptr, 0, stream);
+            right_pad_kernel<<<grid, block, 0, stream>>>(m, p, g_row0, g_rows, Rt, ld1);
+        }
+        h->launches++;
+        trsm_fwd_t(h, N1, g_rows, inner, ld1, dinv, Rt, ld1, stream);                         // sol^T rows = right^T rows inner^-1
+        trsm_bwd_t(h, N1, g_rows, Lt, ld1, dinvT, Rt, ld1, stream);
+        // cross = [Gyx | Gyu]  (K_mn_out K_mn_in^T, regressors.py:153), concatenated so that its rows are contraction-contiguous
+        NK_CUDA(h, cudaMemcpy2DAsync(cross, (size_t)ld1 * 8, G->Gyx, (size_t)G->ld_gyx * 8, (size_t)m * 8, m, cudaMemcpyDeviceToDevice, stream));
+        if (p) NK_CUDA(h, cudaMemcpy2DAsync(cross + m, (size_t)ld1 * 8, G->Gyu, (size_t)G->ld_gyu * 8, (size_t)p * 8, m, cudaMemcpyDeviceToDevice, stream));
+        if (ld1 > N1) NK_CUDA(h, cudaMemset2DAsync(cross + N1, (size_t)ld1 * 8, 0, (size_t)(ld1 - N1) * 8, m, stream));
+        // G^T rows = (sol^T rows cross^T) S^-1      [G = S^-1 (cross sol)]
+        gemm_nt(h, g_rows, m, N1, 1.0, Rt, ld1, cross, ld1, 0.0, T1, ldm, 0.0, 0, nullptr, 0, stream);
+        gemm_nt(h, g_rows, m, m, 1.0, T1, ldm, L->Sinv, L->ld_sinv, 0.0, GT, ld_gt, 0.0, 0, nullptr, 0, stream);
+    }
 
-    // ---- reconstruction: C = GYy (gn Kmm + Gyy)^-1 S,  W = C G   (regressors.py:162-167) ----
-    double *rec = inner;           // reuse (m x ldm fits)
-    double *Lt2 = Lt;
-    double *Pt = Rt;               // (m x ldm)
-    launch2d(m, m, grid, block);
-    assemble_rec_kernel<<<grid, block, 0, stream>>>(m, gamma_n, jitter, Gyy, Kzz, rec, ldm);
-    h->launches++;
-    potrf_blocked(h, m, rec, ldm, Lt2, ldm, dinv, dinvT, dinfo, stream);
-    NK_CUDA(h, cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    NK_CUDA(h, cudaStreamSynchronize(stream));
-    if (hinfo != 0) { if (info) *info = 2; return set_err(h, NK_E_NOT_SPD, "nk_solve_abc: inner_term_rec is not positive definite (pivot " + std::to_string(hinfo) + ")"); }
-    NK_CUDA(h, cudaMemcpy2DAsync(Pt, (size_t)ldm * 8, S, (size_t)m * 8, (size_t)m * 8, m, cudaMemcpyDeviceToDevice, stream));   // S^T = S
-    trsm_fwd_t(h, m, m, rec, ldm, dinv, Pt, ldm, stream);
-    trsm_bwd_t(h, m, m, Lt2, ldm, dinvT, Pt, ldm, stream);                                       // Pt = (inner_rec^-1 S)^T
-    gemm_nt(h, d, m, m, 1.0, GYy, m, Pt, ldm, 0.0, C, m, 0.0, 0, nullptr, 0, stream);           // C = GYy P
-    gemm_nt(h, d, N1, m, 1.0, C, m, Gt, ldm, 0.0, W, N1, 0.0, 0, nullptr, 0, stream);           // W = C G
+    // ---- reconstruction: C = GYy (gn Kmm + Gyy)^-1 S   (regressors.py:162-166), rows of C^T = columns of C ----
+    if (c_rows > 0) {
+        double *rec = inner, *Lt2 = Lt, *Pt = Rt;
+        launch2d(m, m, grid, block);
+        assemble_rec_kernel<<<grid, block, 0, stream>>>(m, gamma_n, jitter, G->Gyy, G->ld_gyy, L->Kzz, L->ld_kzz, rec, ldm);
+        h->launches++;
+        potrf_blocked(h, m, rec, ldm, Lt2, ldm, dinv, dinvT, dinfo + 1, stream);
+        NK_CUDA(h, cudaMemcpy2DAsync(Pt, (size_t)ldm * 8, L->S + (long long)c_row0 * L->ld_s, (size_t)L->ld_s * 8, (size_t)m * 8, c_rows,
+                                     cudaMemcpyDeviceToDevice, stream));                         // rows of S^T = S
+        trsm_fwd_t(h, m, c_rows, rec, ldm, dinv, Pt, ldm, stream);
+        trsm_bwd_t(h, m, c_rows, Lt2, ldm, dinvT, Pt, ldm, stream);                              // rows of (inner_rec^-1 S)^T
+        gemm_nt(h, c_rows, d, m, 1.0, Pt, ldm, G->GYy, G->ld_gYy, 0.0, CT, ld_ct, 0.0, 0, nullptr, 0, stream);   // C^T rows
+    }
+    int hinfo[2] = {0, 0};
+    NK_CUDA(h, cudaMemcpyAsync(hinfo, dinfo, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    NK_CUDA(h, cudaStreamSynchronize(stream));      // the one synchronisation of this call: the two Cholesky verdicts
+    NK_CUDA(h, cudaGetLastError());
+    if ((rc = gram_watchdog_verdict(h)) != NK_OK) return rc;
+    if (hinfo[0] != 0) { if (info) *info = 1; return set_err(h, NK_E_NOT_SPD, "nk_solve_abc: inner_term is not positive definite (pivot " + std::to_string(hinfo[0]) + ")"); }
+    if (hinfo[1] != 0) { if (info) *info = 2; return set_err(h, NK_E_NOT_SPD, "nk_solve_abc: inner_term_rec is not positive definite (pivot " + std::to_string(hinfo[1]) + ")"); }
+    return NK_OK;
+}
+
+int nk_solve_abc_finish(nk_handle *h, int m, int p, int d, const double *GT, long long ld_gt, const double *CT, long long ld_ct,
+                        double *A, long long lda, double *B, long long ldb, double *C, long long ldc, double *W, long long ldw, void *stream_) {
+    if (!h) return NK_E_INVALID;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (m < 1 || p < 0 || d < 1 || !GT || !CT || ld_gt < m || ld_ct < d || (A && lda < m) || (p && B && ldb < p) || (C && ldc < m) || (W && (ldw < m + p || !C)))
+        return set_err(h, NK_E_INVALID, "nk_solve_abc_finish: bad argument");
+    NK_ON_DEVICE(h);
+    if (A) transpose(h, m, m, GT, ld_gt, A, lda, stream);                                        // A = G[:, :m]
+    if (p && B) transpose(h, p, m, GT + (long long)m * ld_gt, ld_gt, B, ldb, stream);             // B = G[:, m:]
+    if (C) transpose(h, m, d, CT, ld_ct, C, ldc, stream);
+    if (W) gemm_nt(h, d, m + p, m, 1.0, C, ldc, GT, ld_gt, 0.0, W, ldw, 0.0, 0, nullptr, 0, stream);   // weights = C G (regressors.py:167)
     NK_CUDA(h, cudaGetLastError());
     return NK_OK;
+}
+
+int nk_solve_abc(nk_handle *h, int m, int p, int d, double gamma_n, double jitter, const nk_grams *G, const nk_landmarks *L,
+                 double *A, long long lda, double *B, long long ldb, double *C, long long ldc, double *W, long long ldw, int *info,
+                 void *stream_) {
+    if (!h) return NK_E_INVALID;
+    if (!A || !C || !W || (p && !B)) return set_err(h, NK_E_INVALID, "nk_solve_abc: bad argument");
+    int rc;
+    const int N1 = m + p, ldm = even(m), ldd = even(d);
+    double *GT, *CT;
+    {
+        NK_ON_DEVICE(h);
+        GT = dense_scratch(h, 5, (size_t)N1 * ldm, &rc); if (rc) return rc;
+        CT = dense_scratch(h, 6, (size_t)m * ldd, &rc); if (rc) return rc;
+    }
+    if ((rc = nk_solve_abc_part(h, m, p, d, gamma_n, jitter, G, L, 0, N1, GT, ldm, 0, m, CT, ldd, info, stream_)) != NK_OK) return rc;
+    return nk_solve_abc_finish(h, m, p, d, GT, ldm, CT, ldd, A, lda, B, ldb, C, ldc, W, ldw, stream_);
 }
 
 int nk_kernel_cross(nk_handle *h, const double *Z, long long ldz, int m, int d, const double *inv_ls, int kind,

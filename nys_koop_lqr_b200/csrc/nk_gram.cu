@@ -44,8 +44,17 @@ struct GramSmemCtl {
     QueuedItem iq[kItemQueue];
 };
 
-__device__ __forceinline__ void spin_until_ge(const int *ctr, int target) {
-    while (ld_acquire(ctr) < target) { __nanosleep(64); }
+// Dependence wait with a watchdog.  A wait that outlasts kSpinCap polls (each poll is an L2 round trip plus a 64 ns sleep, i.e.
+// roughly a microsecond: the cap is tens of seconds, a legitimate wait lasts microseconds), or that sees another CTA's timeout,
+// raises *err and returns false: the caller abandons its item, the kernel drains instead of hanging the device, and the host
+// turns the flag into NK_E_STATE at its next synchronising call (nk_gram_status, nk_solve_abc*, nk_cv_weights).
+__device__ __forceinline__ bool spin_until_ge(const int *ctr, int target, int *err) {
+    unsigned it = 0;
+    while (ld_acquire(ctr) < target) {
+        __nanosleep(64);
+        if ((++it & 0xffffu) == 0 && (it >= kSpinCap || ld_acquire(err) != 0)) { atomicExch(err, 1); return false; }
+    }
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -166,14 +175,16 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                     const int par = kMulti ? it.chunk % P.nslots : (it.chunk & 1);
                     const int gen = kMulti ? it.chunk / P.nslots : (it.chunk >> 1);
                     it.slot = par;
+                    bool ok = true;
                     if (it.type == kItemPack) {
                         // buffers of this slot were last read by lift(chunk-S) / syrk(chunk-S)
-                        if (gen >= 1) spin_until_ge(&P.counters[kCtrSyrk + par], gen * syrk_warps_per_chunk);
+                        if (gen >= 1) ok = spin_until_ge(&P.counters[kCtrSyrk + par], gen * syrk_warps_per_chunk, P.err);
                     } else if (it.type == kItemLift) {
-                        spin_until_ge(&P.counters[kCtrPack + par], (gen + 1) * P.n_pk);
+                        ok = spin_until_ge(&P.counters[kCtrPack + par], (gen + 1) * P.n_pk, P.err);
                     } else {
-                        spin_until_ge(&P.counters[kCtrLift + par], (gen + 1) * lift_warps_per_chunk);
+                        ok = spin_until_ge(&P.counters[kCtrLift + par], (gen + 1) * lift_warps_per_chunk, P.err);
                     }
+                    if (!ok) { valid = false; it.type = -1; }      // watchdog: stop this CTA (the flag stops the others)
                     fence_proxy_async();
                 }
                 // ---- publish to the consumer warps ----
@@ -189,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                     const double *Abase, *Bbase; size_t a_stride, b_stride; int nslabs;
                     const int slot = kMulti ? it.slot : (it.chunk & 1);
                     if (it.type == kItemLift) {
-                        Abase = P.ZP + (size_t)it.b * 16 * 128; a_stride = (size_t)(P.MP / kPanel) * 128;
+                        Abase = (it.a ? P.ZP : P.ZPx) + (size_t)it.b * 16 * 128; a_stride = (size_t)(P.MP / kPanel) * 128;
                         Bbase = (it.a ? P.YP[slot] : P.XP[slot]) + (size_t)it.c * 16 * 128; b_stride = (size_t)(P.nk / kPanel) * 128;
                         nslabs = P.KLS;
                     } else {
@@ -385,10 +396,11 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) {
-                    spin_until_ge(ver, it.chunk * kConsumerWarps);
-                    double *gt = P.Gws + (size_t)it.c * (kTile * kTile) + (size_t)warp * 32 * kBlk;
-                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
-                                 ::"l"(gt), "r"(stg), "r"(16384) : "memory");
+                    if (spin_until_ge(ver, it.chunk * kConsumerWarps, P.err)) {
+                        double *gt = P.Gws + (size_t)it.c * (kTile * kTile) + (size_t)warp * 32 * kBlk;
+                        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
+                                     ::"l"(gt), "r"(stg), "r"(16384) : "memory");
+                    }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 pend_ver = ver;

@@ -24,7 +24,8 @@ struct GramParams {
     int psi_rp;    // row panels of Psi (= (2*MP + EP)/8)
     int e_row0;    // first row of the [U;Y] block in Psi (= 2*MP)
     int EP;        // [U;Y] rows padded to a multiple of 128
-    const double *ZP;       // packed, scaled, augmented landmarks: MP/8 panels x KLS slabs
+    const double *ZP;       // packed, scaled, augmented OUTPUT landmarks (lift of x_{t+1}): MP/8 panels x KLS slabs
+    const double *ZPx;      // the same for the INPUT landmarks (lift of x_t); == ZP unless the caller injected distinct input centres
     const double *inv_ls;   // (d) 1/length_scale
     const double *center;   // (d) shift applied to samples and landmarks before the norm expansion
     int nslots;             // chunk buffers in flight: chunk c lives in slot c % nslots (2 for large m; more when one chunk's items
@@ -37,12 +38,14 @@ struct GramParams {
 #ifdef NK_GRAM_TIMING
     long long *timing;      // development build only: 16 cycle counters per consumer warp (tools/gram_timing.py)
 #endif
+    int *err;               // watchdog flag (handle-owned, zeroed by nk_gram_begin): set when a dependence wait timed out
     int *counters;          // [0] next item; per slot s: [kCtrPack+s] packs done, [kCtrLift+s] lift warps done, [kCtrSyrk+s] syrk warps done;
                             // [kCounterTileVer+t] tile versions
 };
 
 constexpr int kCtrPack = 16, kCtrLift = 32, kCtrSyrk = 48;
 constexpr int kCounterTileVer = 64;
+constexpr unsigned kSpinCap = 1u << 25;   // polls of a dependence wait before the watchdog fires (~1 us each)
 constexpr int kGramStages = 3;
 constexpr int kItemQueue = 4;
 constexpr size_t kGramStageBytes = (size_t)kGramStages * 2 * kSlabTileDoubles * 8;      // 96 KB operand ring

@@ -23,8 +23,11 @@ struct nk_handle {
     int MP = 0, KLS = 0, EP = 0, psi_rows = 0, nblk = 0, ntiles = 0;
     int n_pk = 0, n_lf = 0, n_sy = 0, period_len = 0;
     double last_flops = 0.0;
-    nk_devbuf zp, inv_ls, center, xp[nk::kMaxSlots], yp[nk::kMaxSlots], psi[nk::kMaxSlots], gws, items, counters, tile_of;
+    nk_devbuf zp, zp_in, inv_ls, center, xp[nk::kMaxSlots], yp[nk::kMaxSlots], psi[nk::kMaxSlots], gws, items, counters, tile_of;
     int nslots = 2;
+    nk_devbuf gram_err;         // device int: watchdog flag of the fused kernel (nk_gram.cu spin_until_ge)
+    int *gram_err_host = nullptr;   // pinned copy, refreshed by nk_gram_finalize; examined at synchronising calls
+    bool distinct_in = false;   // input landmarks differ from the output landmarks (regressors.py:133-134 allows injecting them)
     std::vector<int> h_tile_of;
 
     // ---- dense-stage scratch (grow-only), see nk_dense.cu ----
@@ -33,6 +36,7 @@ struct nk_handle {
 };
 
 namespace nk {
+int gram_watchdog_verdict(nk_handle *h);   // after a stream synchronisation: NK_E_STATE if the fused kernel's watchdog fired
 int set_err(nk_handle *h, int code, const std::string &msg);
 int check_cuda(nk_handle *h, cudaError_t e, const char *what);
 int ensure(nk_handle *h, nk_devbuf &b, size_t bytes);

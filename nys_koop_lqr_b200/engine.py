@@ -122,12 +122,24 @@ class Engine:
         return int(self.lib.nk_device_sm_count(self.h))
 
     # ------------------------------------------------------------------ fused lift + Grams
-    def gram_begin(self, Z, inv_ls, kind, p, chunk=0):
+    def gram_begin(self, Z, inv_ls, kind, p, chunk=0, Z_in=None):
+        """Z: (m, d) output landmarks; Z_in: distinct input landmarks (m, d) or None (regressors.py:133-134)."""
         _f64(Z, "Z"); _f64(inv_ls, "inv_ls")
         m, d = Z.shape
         self._gram_shape = (m, d, int(p))
-        self._ck(self.lib.nk_gram_begin(self.h, _ptr(Z), Z.stride(0), m, d, int(p), _ptr(inv_ls), int(kind), int(chunk),
-                                        self._stream()), "nk_gram_begin")
+        if Z_in is None:
+            self._ck(self.lib.nk_gram_begin(self.h, _ptr(Z), Z.stride(0), m, d, int(p), _ptr(inv_ls), int(kind), int(chunk),
+                                            self._stream()), "nk_gram_begin")
+        else:
+            _f64(Z_in, "Z_in")
+            if tuple(Z_in.shape) != (m, d):
+                raise ValueError("input and output landmark sets must have the same shape")
+            self._ck(self.lib.nk_gram_begin_io(self.h, _ptr(Z_in), Z_in.stride(0), _ptr(Z), Z.stride(0), m, d, int(p), _ptr(inv_ls),
+                                               int(kind), int(chunk), self._stream()), "nk_gram_begin_io")
+
+    def gram_status(self):
+        """Synchronises the current stream; raises NkError if the fused kernel's dependence-wait watchdog fired."""
+        self._ck(self.lib.nk_gram_status(self.h, self._stream()), "nk_gram_status")
 
     def gram_update(self, X_aug, Y):
         """X_aug (n, d+p) [state | controls], Y (n, d); row stride may exceed the width (views of wider buffers)."""
@@ -177,8 +189,8 @@ class Engine:
             o += a * b
         return out
 
-    def grams(self, X_aug, Y, Z, inv_ls, kind, p, chunk=0):
-        self.gram_begin(Z, inv_ls, kind, p, chunk)
+    def grams(self, X_aug, Y, Z, inv_ls, kind, p, chunk=0, Z_in=None):
+        self.gram_begin(Z, inv_ls, kind, p, chunk, Z_in=Z_in)
         self.gram_update(X_aug, Y)
         return self.gram_finalize()
 
@@ -251,20 +263,68 @@ class Engine:
         self.last_sqrt_iters = iters.value
         return S, Sinv
 
-    def solve_abc(self, G, Kzz, S, Sinv, gamma_n, jitter=JITTER):
+    # -- struct marshalling (include/nk_b200.h: nk_grams, nk_landmarks) --
+    @staticmethod
+    def _mat(t, name, rows=None, cols=None):
+        if t is None:
+            return C.c_void_p(0), 0
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] <= 1)):
+            raise TypeError(f"{name} must be a float64 CUDA matrix with unit column stride")
+        if t.numel() == 0:
+            return C.c_void_p(0), max(1, t.shape[1])
+        return C.c_void_p(t.data_ptr()), max(int(t.stride(0)), int(t.shape[1]), 1)
+
+    def _grams_struct(self, G):
+        g = _lib.NkGrams()
+        for k in ("Gxx", "Gyx", "Gyy", "Gxu", "Gyu", "Guu", "GYy"):
+            ptr, ld = self._mat(G[k], k)
+            setattr(g, k, ptr)
+            setattr(g, "ld_" + k[0].lower() + k[1:], ld)
+        return g
+
+    def _landmarks_struct(self, Kzz, S, Sinv, Kzz_in=None, Kio=None):
+        lm = _lib.NkLandmarks()
+        lm.Kzz, lm.ld_kzz = self._mat(Kzz, "Kzz")
+        lm.S, lm.ld_s = self._mat(S, "S")
+        lm.Sinv, lm.ld_sinv = self._mat(Sinv, "Sinv")
+        lm.Kzz_in, lm.ld_kzz_in = self._mat(Kzz_in, "Kzz_in")
+        lm.Kio, lm.ld_kio = self._mat(Kio, "Kio")
+        return lm
+
+    def solve_abc(self, G, Kzz, S, Sinv, gamma_n, jitter=JITTER, Kzz_in=None, Kio=None):
+        """Grams -> A (m,m), B (m,p), C (d,m), W (d,m+p) (regressors.py:147-169).  Kzz_in / Kio: k(Z_in,Z_in), k(Z_in,Z_out) when the
+        input landmarks differ from the output landmarks."""
         m = Kzz.shape[0]
         p = G["Guu"].shape[0]
         d = G["GYy"].shape[0]
         A, B, Cm, W = self.empty(m, m), self.empty(m, p), self.empty(d, m), self.empty(d, m + p)
         info = C.c_int(0)
-        names = ("Gxx", "Gyx", "Gyy", "Gxu", "Gyu", "Guu", "GYy")
-        for k in names:
-            if G[k].numel():
-                _f64(G[k], k)
-        ptrs = [_ptr(G[k]) if G[k].numel() else C.c_void_p(0) for k in names]
-        self._ck(self.lib.nk_solve_abc(self.h, m, p, d, float(gamma_n), float(jitter), *ptrs, _ptr(_f64(Kzz, "Kzz")),
-                                       _ptr(_f64(S, "S")), _ptr(_f64(Sinv, "Sinv")), _ptr(A), _ptr(B) if p else C.c_void_p(0),
-                                       _ptr(Cm), _ptr(W), C.byref(info), self._stream()), "nk_solve_abc")
+        g, lm = self._grams_struct(G), self._landmarks_struct(Kzz, S, Sinv, Kzz_in, Kio)
+        self._ck(self.lib.nk_solve_abc(self.h, m, p, d, float(gamma_n), float(jitter), C.byref(g), C.byref(lm), _ptr(A), m,
+                                       _ptr(B) if p else C.c_void_p(0), max(p, 1), _ptr(Cm), m, _ptr(W), m + p, C.byref(info),
+                                       self._stream()), "nk_solve_abc")
+        return A, B, Cm, W
+
+    def solve_abc_part(self, G, Kzz, S, Sinv, gamma_n, g_rows, c_rows, GT, CT, jitter=JITTER, Kzz_in=None, Kio=None):
+        """A slice of the solve for sharding over devices: rows g_rows = (start, count) of G^T ((m+p, m): row c = column c of [A|B])
+        are written to GT[:count], rows c_rows of C^T ((m, d)) to CT[:count].  Every device factors both systems and solves only
+        its columns (include/nk_b200.h nk_solve_abc_part)."""
+        m = Kzz.shape[0]
+        p = G["Guu"].shape[0]
+        d = G["GYy"].shape[0]
+        info = C.c_int(0)
+        g, lm = self._grams_struct(G), self._landmarks_struct(Kzz, S, Sinv, Kzz_in, Kio)
+        self._ck(self.lib.nk_solve_abc_part(self.h, m, p, d, float(gamma_n), float(jitter), C.byref(g), C.byref(lm),
+                                            int(g_rows[0]), int(g_rows[1]), _ptr(GT), GT.stride(0) if GT is not None else 0,
+                                            int(c_rows[0]), int(c_rows[1]), _ptr(CT), CT.stride(0) if CT is not None else 0,
+                                            C.byref(info), self._stream()), "nk_solve_abc_part")
+
+    def solve_abc_finish(self, GT, CT, m, p, d):
+        """Assembled G^T (m+p, m) and C^T (m, d) -> A, B, C, W = C G on this device."""
+        A, B, Cm, W = self.empty(m, m), self.empty(m, p), self.empty(d, m), self.empty(d, m + p)
+        self._ck(self.lib.nk_solve_abc_finish(self.h, m, p, d, _ptr(GT), GT.stride(0), _ptr(CT), CT.stride(0), _ptr(A), m,
+                                              _ptr(B) if p else C.c_void_p(0), max(p, 1), _ptr(Cm), m, _ptr(W), m + p, self._stream()),
+                 "nk_solve_abc_finish")
         return A, B, Cm, W
 
     def closed_loop(self, A, B, Cm, K, Z0, Zref, steps, return_final=False):
@@ -297,9 +357,9 @@ class Engine:
         Wk = self.empty(nlam, d, m + p)
         gn = (C.c_double * nlam)(*[float(g) for g in gamma_n])
         info = (C.c_int * nlam)()
-        names = ("Gxx", "Gyx", "Gyy", "Gxu", "Gyu", "Guu", "GYy")
-        ptrs = [_ptr(_f64(G[k], k)) if G[k].numel() else C.c_void_p(0) for k in names]
-        rc = self.lib.nk_cv_weights(self.h, m, p, d, nlam, gn, float(jitter), *ptrs, _ptr(_f64(Kzz, "Kzz")), _ptr(Wk), info, self._stream())
+        g = self._grams_struct(G)
+        kptr, kld = self._mat(Kzz, "Kzz")
+        rc = self.lib.nk_cv_weights(self.h, m, p, d, nlam, gn, float(jitter), C.byref(g), kptr, kld, _ptr(Wk), m + p, info, self._stream())
         if rc not in (0, -3):      # NK_E_NOT_SPD is reported per value through info (sklearn's error_score=nan semantics)
             self._ck(rc, "nk_cv_weights")
         return Wk, list(info)

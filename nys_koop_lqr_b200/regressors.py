@@ -137,6 +137,42 @@ def _host_copy(src, threads=None):
     return dst
 
 
+def _fingerprint(a):
+    """Cheap content key of a (small) numpy array: the device-side cache must notice IN-PLACE edits (sklearn kernels are
+    mutable, callers assign into the centre arrays), which object identity does not."""
+    if a is None:
+        return None
+    a = np.asarray(a)
+    if a.nbytes <= (64 << 20):
+        return (a.shape, a.dtype.str, zlib.crc32(np.ascontiguousarray(a).view(np.uint8).reshape(-1)))
+    flat = a.reshape(-1)
+    step = max(1, flat.size // (1 << 20))
+    return (a.shape, a.dtype.str, zlib.crc32(np.ascontiguousarray(flat[::step]).view(np.uint8)), float(flat.sum()))
+
+
+def _lazy_result(name):
+    """A / B / C / weights: plain numpy attributes for callers (as upstream), backed by a pending DEVICE result after a
+    sharded fit -- the download happens on first access, on the ranks that look (results once per node)."""
+    key = "_" + name
+
+    def getter(self):
+        v = self.__dict__.get(key)
+        if v is None and name in (self.__dict__.get("_pending") or {}):
+            self._materialize()
+            v = self.__dict__.get(key)
+        return v
+
+    def setter(self, v):
+        self.__dict__[key] = v
+        pend = self.__dict__.get("_pending")
+        if pend:
+            pend.pop(name, None)
+        if name == "weights" and self.__dict__.get("_dev"):
+            self.__dict__["_dev"]["W"] = None          # assigned / loaded weights: the device copy used by predict is stale
+
+    return property(getter, setter)
+
+
 class KoopmanNystromRegressor(KoopmanRegressor):
     """Nystrom-Koopman estimator (regressors.py:114-178) on the B200 kernels.
 
@@ -157,26 +193,58 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         self.nystrom_centers_output = None
         self.jitter = 1e-6
 
+    A = _lazy_result("A")
+    B = _lazy_result("B")
+    C = _lazy_result("C")
+    weights = _lazy_result("weights")
+
     # -- device-side cache (never pickled) ------------------------------------------------------
     def __getstate__(self):
+        self._materialize()
         state = dict(self.__dict__)
         state.pop("_dev", None)
+        state.pop("_pending", None)
+        for k in ("A", "B", "C", "weights"):          # plain attribute names in the pickle, as the reference class writes them
+            state[k] = state.pop("_" + k, None)
         return state
 
+    def __setstate__(self, state):
+        state = dict(state)
+        for k in ("A", "B", "C", "weights"):          # also accepts pickles written by the reference class itself
+            if k in state:
+                state["_" + k] = state.pop(k)
+        self.__dict__.update(state)
+
+    def _distinct_input_centers(self):
+        zi, zo = self.nystrom_centers_input, self.nystrom_centers_output
+        return zi is not None and zi is not zo and not np.array_equal(zi, zo)
+
+    def _cache_key(self, n_states):
+        kind, ls = kernel_spec(self.kernel, n_states)
+        zi = self.nystrom_centers_input if self._distinct_input_centers() else None
+        return (kind, tuple(ls.tolist()), float(self.jitter), _fingerprint(self.nystrom_centers_output), _fingerprint(zi))
+
     def _device_state(self, n_states, landmark_stage=True):
-        """Landmarks, 1/l, K_zz, S, S^-1 on the device; rebuilt lazily (e.g. after unpickling).  With
-        ``landmark_stage=False`` only the landmarks and 1/l are set up (K_zz, S, S^-1 are filled in later: the
-        sample-sharded fit computes them on one rank and broadcasts them)."""
+        """Landmarks, 1/l, K_zz, S, S^-1 on the device; rebuilt lazily (e.g. after unpickling) and whenever the kernel's
+        hyper-parameters, the jitter or the CONTENTS of the centre arrays change (the key is by value, not identity: sklearn
+        kernels and the centre arrays are mutable).  With ``landmark_stage=False`` only the landmarks and 1/l are set up (K_zz,
+        S, S^-1 are filled in later: the sample-sharded fit computes them on one rank and broadcasts them)."""
         import torch
+        key = self._cache_key(n_states)
         dev = self.__dict__.get("_dev")
-        Zc = self.nystrom_centers_output
-        if dev is not None and dev["src"] is Zc and dev["kernel"] is self.kernel and (dev.get("S") is not None or not landmark_stage):
+        if dev is not None and dev["key"] == key and (dev.get("S") is not None or not landmark_stage):
             return dev
         eng = _engine()
         kind, ls = kernel_spec(self.kernel, n_states)
-        Z = torch.from_numpy(np.ascontiguousarray(np.asarray(Zc, dtype=np.float64).T)).to(eng.tdev)   # (m, d) rows
+        rows = lambda c: torch.from_numpy(np.ascontiguousarray(np.asarray(c, dtype=np.float64).T)).to(eng.tdev)   # (m, d) rows
+        Z = rows(self.nystrom_centers_output)
+        if Z.shape[1] != n_states:
+            raise ValueError(f"landmarks have {Z.shape[1]} state dimensions, the data {n_states}")
+        Z_in = rows(self.nystrom_centers_input) if self._distinct_input_centers() else None
+        if Z_in is not None and tuple(Z_in.shape) != tuple(Z.shape):
+            raise ValueError("nystrom_centers_input and nystrom_centers_output must have the same shape (regressors.py:143 adds jitter * eye(m))")
         inv_ls = torch.from_numpy(1.0 / ls).to(eng.tdev)
-        dev = dict(src=Zc, kernel=self.kernel, eng=eng, kind=kind, ls=ls, Z=Z, inv_ls=inv_ls, Kzz=None, S=None, Sinv=None)
+        dev = dict(key=key, eng=eng, kind=kind, ls=ls, Z=Z, Z_in=Z_in, inv_ls=inv_ls, Kzz=None, S=None, Sinv=None, Kzz_in=None, Kio=None)
         if landmark_stage:
             self._landmark_stage(dev)
         self.__dict__["_dev"] = dev
@@ -184,26 +252,27 @@ class KoopmanNystromRegressor(KoopmanRegressor):
 
     def _landmark_stage(self, dev):
         """K_zz (regressors.py:144), K_mm = K_zz + jitter I (:139,143), S = K_mm^(1/2) and S^-1 (:140,152-153,163): the part
-        of the fit that depends on the landmarks only."""
+        of the fit that depends on the landmarks only.  With distinct input landmarks also k(Z_in, Z_in) (:143) and
+        k(Z_in, Z_out) (:144)."""
         eng = dev["eng"]
         Kzz = eng.kzz(dev["Z"], dev["inv_ls"], dev["kind"])
         Kmm = Kzz.clone()
         Kmm.diagonal().add_(self.jitter)
         S, Sinv = eng.sym_sqrt(Kmm, lambda_min_bound=self.jitter)
         dev.update(Kzz=Kzz, S=S, Sinv=Sinv)
+        if dev["Z_in"] is not None:
+            dev["Kzz_in"] = eng.kzz(dev["Z_in"], dev["inv_ls"], dev["kind"])
+            dev["Kio"] = eng.kernel_cross(dev["Z_in"], dev["Z"], dev["inv_ls"], dev["kind"])     # (m, m): rows = input landmarks
 
     # -- landmarks --------------------------------------------------------------------------------
     def _ensure_centers(self, Y_rows_getter, n):
         """regressors.py:129-134: one np.random.choice draw on the global legacy RNG, landmarks are next-state
-        samples, input centres alias the output centres; persisted so a refit reuses them."""
+        samples, input centres alias the output centres unless the caller injected its own; persisted so a refit reuses them."""
         if self.nystrom_centers_output is None:
             idx = np.random.choice(np.arange(0, n), size=self.m, replace=False)
             self.nystrom_centers_output = Y_rows_getter(idx)          # (d, m)
         if self.nystrom_centers_input is None:
             self.nystrom_centers_input = self.nystrom_centers_output
-        if self.nystrom_centers_input is not self.nystrom_centers_output and not np.array_equal(
-                self.nystrom_centers_input, self.nystrom_centers_output):
-            raise NotImplementedError("distinct input/output landmark sets are not implemented on the GPU path")
         self.m = int(np.asarray(self.nystrom_centers_output).shape[1]) if self.m is None else self.m
 
     @staticmethod
@@ -219,7 +288,7 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         """Streams (X, Y) through the fused lift+Gram kernel. Host inputs go up in double-buffered blocks."""
         import torch
         n = X.shape[0]
-        eng.gram_begin(dev["Z"], dev["inv_ls"], dev["kind"], self.n_inputs, self.gram_chunk)
+        eng.gram_begin(dev["Z"], dev["inv_ls"], dev["kind"], self.n_inputs, self.gram_chunk, Z_in=dev["Z_in"])
         on_device = isinstance(X, torch.Tensor) and X.is_cuda and isinstance(Y, torch.Tensor) and Y.is_cuda
         if on_device:
             Xd, Yd = _as_device_rows(eng, X), _as_device_rows(eng, Y)
@@ -256,38 +325,74 @@ class KoopmanNystromRegressor(KoopmanRegressor):
             freed[b].record(main)
         self._h2d_bytes = int(n) * (wx + wy) * 8
 
-    def _solve(self, eng, dev, G, n_total, d):
-        """Grams -> A, B, C, weights on the device (nk_solve_abc), then numpy copies on the host.  A and B are complete when
-        nk_solve_abc returns (include/nk_b200.h), so their download and host copy run on a side stream / host threads while the
-        device is still finishing C and the weights."""
+    # -- Grams -> A, B, C, weights ------------------------------------------------------------------
+    @staticmethod
+    def _shift_grams(G, scale=64.0):
+        """Tikhonov retry for a numerically indefinite regularised system: add delta = scale * eps * max diagonal entry to the
+        diagonals of G_xx, G_uu, G_yy (i.e. to inner_term and inner_term_rec).  The reference's lstsq (LAPACK gelsd, rcond = eps)
+        discards the directions below eps * sigma_max instead; both regularise the same near-null space.  Stated deviation."""
         import torch
-        gamma_n = float(self.gamma) * float(n_total)                 # regressors.py:127
-        A, B, C, W = eng.solve_abc(G, dev["Kzz"], dev["S"], dev["Sinv"], gamma_n, self.jitter)
-        dev["W"] = W
-        total = A.numel() + B.numel() + C.numel() + W.numel()
-        host = eng.pinned_staging(total)                             # grow-only pinned buffer owned by the engine (cudaHostAlloc is slow)
+        delta = scale * float(np.finfo(np.float64).eps) * float(torch.maximum(G["Gxx"].diagonal().max(), G["Gyy"].diagonal().max()))
+        for k in ("Gxx", "Gyy", "Guu"):
+            if G[k].numel():
+                G[k].diagonal().add_(delta)
+        return delta
+
+    def _solve_guarded(self, fn, G):
+        """Runs a solve; if a regularised system is not positive definite in float64 (cond >~ 1e16: the tiniest gammas of the
+        scripts' grids), retries once with a diagonal shift (see _shift_grams) and records it in ``spd_shift_``."""
+        from ._lib import NkError
+        self.spd_shift_ = 0.0
+        try:
+            return fn()
+        except NkError as exc:
+            if "not positive definite" not in str(exc):
+                raise
+            import warnings
+            self.spd_shift_ = self._shift_grams(G)
+            warnings.warn(f"KoopmanNystromRegressor: regularised system not positive definite in float64; retrying with a diagonal "
+                          f"shift of {self.spd_shift_:.3e} (the reference's lstsq truncates those directions instead)", RuntimeWarning)
+            return fn()
+
+    def _set_device_results(self, dev, A, B, C, W, eager):
+        dev["W"], dev["W_src"] = W, None
+        self.__dict__["_pending"] = dict(A=A, B=B, C=C, weights=W)
+        for k in ("A", "B", "C", "weights"):
+            self.__dict__["_" + k] = None
+        if eager:
+            self._materialize()
+
+    def _materialize(self):
+        """Pending device results -> numpy attributes: one pinned staging buffer (engine-owned, grow-only), A and B on a side
+        stream, first-touch host copies of the large matrices by a few threads."""
+        pend = self.__dict__.get("_pending")
+        if not pend:
+            return
+        import torch
+        eng = self.__dict__["_dev"]["eng"] if self.__dict__.get("_dev") else _engine()
+        names = [k for k in ("A", "B", "C", "weights") if k in pend]
+        tensors = [pend[k] for k in names]
+        total = sum(t.numel() for t in tensors)
+        host = eng.pinned_staging(total)
         main = torch.cuda.current_stream(eng.tdev)
-        side = eng.side_stream()
-        o = 0
-        slots = []
-        for t in (A, B, C, W):
+        o, slots = 0, []
+        for t in tensors:
             slots.append((o, tuple(t.shape)))
+            host[o:o + t.numel()].copy_(t.reshape(-1), non_blocking=True)
             o += t.numel()
-        done_ab = torch.cuda.Event()
-        with torch.cuda.stream(side):
-            for t, (off, _) in zip((A, B), slots[:2]):
-                t.record_stream(side)
-                host[off:off + t.numel()].copy_(t.reshape(-1), non_blocking=True)
-            done_ab.record(side)
-        for t, (off, _) in zip((C, W), slots[2:]):
-            host[off:off + t.numel()].copy_(t.reshape(-1), non_blocking=True)
-        arr = host.numpy()
-        take = lambda k: _host_copy(arr[slots[k][0]:slots[k][0] + int(np.prod(slots[k][1]))].reshape(slots[k][1]))
-        done_ab.synchronize()
-        self.A, self.B = take(0), take(1)
         main.synchronize()
-        self.C, self.weights = take(2), take(3)
+        arr = host.numpy()
+        for k, (off, shape) in zip(names, slots):
+            self.__dict__["_" + k] = _host_copy(arr[off:off + int(np.prod(shape))].reshape(shape))
         self._d2h_bytes = int(total) * 8
+        self.__dict__["_pending"] = {}
+
+    def _solve(self, eng, dev, G, n_total, d):
+        """Grams -> A, B, C, weights on the device (nk_solve_abc), then numpy copies on the host."""
+        gamma_n = float(self.gamma) * float(n_total)                 # regressors.py:127
+        A, B, C, W = self._solve_guarded(lambda: eng.solve_abc(G, dev["Kzz"], dev["S"], dev["Sinv"], gamma_n, self.jitter,
+                                                               Kzz_in=dev["Kzz_in"], Kio=dev["Kio"]), G)
+        self._set_device_results(dev, A, B, C, W, eager=True)
 
     # -- public API -------------------------------------------------------------------------------
     def fit(self, X, Y):
@@ -306,44 +411,107 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         G = eng.gram_finalize()
         self._solve(eng, dev, G, n, d)
 
-    def fit_distributed(self, X_local, Y_local, group=None, head_rank=0):
-        """Sample-sharded fit: every rank holds a contiguous block of samples; landmarks are drawn with
-        the reference's call over the GLOBAL sample index (all ranks must share the numpy global RNG state), the
-        local Grams are summed with ONE allreduce, and every rank then solves redundantly (identical results).
+    # -- helpers of the multi-process paths ---------------------------------------------------------
+    @staticmethod
+    def _agree(group, device, fn, what):
+        """Runs a rank-local stage and makes its outcome collective: a failure on ANY rank (NkError from the library, a shape
+        error, ...) raises on EVERY rank before the next data collective, instead of leaving the others blocked in it."""
+        import torch
+        import torch.distributed as dist
+        err, out = None, None
+        try:
+            out = fn()
+        except Exception as exc:  # noqa: BLE001
+            err = exc
+        flag = torch.tensor([1 if err is not None else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        if int(flag.item()):
+            if err is not None:
+                raise err
+            from ._lib import NkError
+            raise NkError(f"{what}: failed on another rank")
+        return out
 
-        The landmark-only stage (K_zz, the symmetric square root S and S^-1) is computed by ``head_rank`` alone, after its
-        own Gram pass, and broadcast -- the other ranks are still streaming samples then if the head's shard is smaller by
-        ``sharding.head_samples(m, d, p)`` (see ``sharding.balanced_bounds``).  ``head_rank=None``: every rank computes it."""
+    def _draw_shared_landmarks(self, n_total, off, n_local, Y_local, d, group, device):
+        """regressors.py:129-132 over the GLOBAL sample index.  Every rank makes the reference's draw (so that each process's
+        legacy RNG advances exactly as in a single-process run), but rank 0's indices are the ones used: they are broadcast, so
+        ranks whose numpy RNG states differ still assemble ONE landmark set."""
+        import torch
+        import torch.distributed as dist
+        from . import sharding
+        idx = np.random.choice(np.arange(0, n_total), size=self.m, replace=False)
+        t = torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int64)).to(device)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        idx = t.cpu().numpy()
+        rows_of = lambda loc: torch.from_numpy(np.ascontiguousarray(self._rows_to_centers(Y_local, loc).T))
+        Z = sharding.assemble_landmarks(idx, off, n_local, rows_of, d, group, device)
+        self.nystrom_centers_output = np.ascontiguousarray(Z.cpu().numpy().T)
+
+    def fit_distributed(self, X_local, Y_local, group=None, head_rank=0, materialize="lazy"):
+        """Sample-sharded fit: every rank holds a contiguous block of samples; landmarks are drawn with the
+        reference's call over the GLOBAL sample index (rank 0's draw, broadcast), the local Grams are summed with ONE allreduce
+        -- the only collective on the n-proportional path.
+
+        What does not shrink with the rank count is kept off the critical path:
+          * the landmark-only stage (K_zz, the symmetric square root S and S^-1) is computed by ``head_rank`` alone, after its
+            own Gram pass, and broadcast -- the other ranks are still streaming samples then if the head's shard is smaller by
+            ``sharding.head_samples(m, d, p)`` (``sharding.balanced_bounds``); ``head_rank=None``: every rank computes it;
+          * the two regularised solves are SHARDED by right-hand-side column: every rank factors both systems, solves (m+p)/G
+            columns of [A|B] and m/G columns of C (``nk_solve_abc_part``), and two all-gathers assemble G^T and C^T;
+          * the results stay on the device until somebody reads them: ``materialize="lazy"`` (default) downloads A / B / C /
+            weights on first attribute access on the ranks that look, ``"all"`` downloads on every rank before returning."""
         import torch
         import torch.distributed as dist
         from . import sharding
         eng = _engine()
         n_local = int(X_local.shape[0])
         d = int(X_local.shape[1]) - self.n_inputs
+        p = self.n_inputs
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
         n_total, off = sharding.global_layout(n_local, group, eng.tdev)
         if self.nystrom_centers_output is None:
-            idx = np.random.choice(np.arange(0, n_total), size=self.m, replace=False)
-            rows_of = lambda loc: torch.from_numpy(np.ascontiguousarray(self._rows_to_centers(Y_local, loc).T))
-            Z = sharding.assemble_landmarks(idx, off, n_local, rows_of, d, group, eng.tdev)
-            self.nystrom_centers_output = np.ascontiguousarray(Z.cpu().numpy().T)
+            self._draw_shared_landmarks(n_total, off, n_local, Y_local, d, group, eng.tdev)
         self._ensure_centers(None, n_total)
-        world = dist.get_world_size(group)
         split = head_rank is not None and world > 1
-        dev = self._device_state(d, landmark_stage=not split)
-        self._accumulate_grams(eng, dev, X_local, Y_local)
-        G = eng.gram_finalize()
-        if split and dev.get("S") is None:
-            m = dev["Z"].shape[0]
-            lm = torch.empty(3, m, m, dtype=torch.float64, device=eng.tdev)
-            if dist.get_rank(group) == head_rank:
-                self._landmark_stage(dev)
-                lm[0].copy_(dev["Kzz"]); lm[1].copy_(dev["S"]); lm[2].copy_(dev["Sinv"])
-            sharding.allreduce_grams(G["_flat"], group)                           # the only data-path collective
+
+        def local_stage():
+            dev = self._device_state(d, landmark_stage=not split)
+            self._accumulate_grams(eng, dev, X_local, Y_local)
+            G = eng.gram_finalize()
+            lm = None
+            if split and dev.get("S") is None:
+                m = dev["Z"].shape[0]
+                nmat = 5 if dev["Z_in"] is not None else 3
+                lm = torch.empty(nmat, m, m, dtype=torch.float64, device=eng.tdev)
+                if rank == head_rank:
+                    self._landmark_stage(dev)
+                    for i, k in enumerate(("Kzz", "S", "Sinv", "Kzz_in", "Kio")[:nmat]):
+                        lm[i].copy_(dev[k])
+            return dev, G, lm
+        dev, G, lm = self._agree(group, eng.tdev, local_stage, "fit_distributed: Gram pass / landmark stage")
+        sharding.allreduce_grams(G["_flat"], group)                                   # the only data-path collective
+        if lm is not None:
             dist.broadcast(lm, src=dist.get_global_rank(group, head_rank) if group is not None else head_rank, group=group)
             dev.update(Kzz=lm[0], S=lm[1], Sinv=lm[2])
-        else:
-            sharding.allreduce_grams(G["_flat"], group)
-        self._solve(eng, dev, G, n_total, d)
+            if lm.shape[0] == 5:
+                dev.update(Kzz_in=lm[3], Kio=lm[4])
+        # ---- column-sharded solve ----
+        m = dev["Z"].shape[0]
+        N1 = m + p
+        g_per, g0, gc = sharding.solve_row_ranges(N1, world, rank)
+        c_per, c0, cc = sharding.solve_row_ranges(m, world, rank)
+        g_rows, c_rows = (g0, gc), (c0, cc)
+        GT_all = torch.zeros(world * g_per, m, dtype=torch.float64, device=eng.tdev)
+        CT_all = torch.zeros(world * c_per, d, dtype=torch.float64, device=eng.tdev)
+        GT_mine, CT_mine = GT_all[rank * g_per:(rank + 1) * g_per], CT_all[rank * c_per:(rank + 1) * c_per]
+        gamma_n = float(self.gamma) * float(n_total)                                  # regressors.py:127
+        part = lambda: eng.solve_abc_part(G, dev["Kzz"], dev["S"], dev["Sinv"], gamma_n, g_rows, c_rows, GT_mine, CT_mine, self.jitter,
+                                          Kzz_in=dev["Kzz_in"], Kio=dev["Kio"])
+        self._agree(group, eng.tdev, lambda: self._solve_guarded(part, G), "fit_distributed: regularised solves")
+        sharding.gather_rows(GT_all, GT_mine, group)
+        sharding.gather_rows(CT_all, CT_mine, group)
+        A, B, C, W = eng.solve_abc_finish(GT_all, CT_all, m, p, d)
+        self._set_device_results(dev, A, B, C, W, eager=(materialize == "all"))
 
     def fit_cv(self, X, Y, kernels, gammas, n_splits=5, refit=True):
         """Batched hyper-parameter search: the reference's ``learn_hyperparams`` (benchmark_lqr_cloth.py:39-66,
@@ -370,6 +538,8 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         if int(Y.shape[0]) != n or int(Y.shape[1]) != d:
             raise ValueError("X must be (n, n_states + n_inputs) and Y (n, n_states)")
         self._ensure_centers(lambda idx: self._rows_to_centers(Y, idx), n)
+        if self._distinct_input_centers():
+            raise NotImplementedError("fit_cv shares one landmark set across candidates and folds; distinct input centres are only supported by fit")
         eng = _engine()
         Xd, Yd = _as_device_rows(eng, X), _as_device_rows(eng, Y)
         sizes = np.full(n_splits, n // n_splits, dtype=int)
@@ -439,11 +609,10 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         p = self.n_inputs
         n_total, off = sharding.global_layout(n_local, group, eng.tdev)
         if self.nystrom_centers_output is None:
-            idx = np.random.choice(np.arange(0, n_total), size=self.m, replace=False)
-            rows_of = lambda loc: torch.from_numpy(np.ascontiguousarray(self._rows_to_centers(Y_local, loc).T))
-            Zc = sharding.assemble_landmarks(idx, off, n_local, rows_of, d, group, eng.tdev)
-            self.nystrom_centers_output = np.ascontiguousarray(Zc.cpu().numpy().T)
+            self._draw_shared_landmarks(n_total, off, n_local, Y_local, d, group, eng.tdev)
         self._ensure_centers(None, n_total)
+        if self._distinct_input_centers():
+            raise NotImplementedError("fit_cv shares one landmark set across candidates and folds; distinct input centres are only supported by fit")
         Xd, Yd = _as_device_rows(eng, X_local), _as_device_rows(eng, Y_local)
         folds = sharding.kfold_bounds(n_total, n_splits)
         local = sharding.fold_local_ranges(n_total, n_splits, off, n_local)
@@ -463,35 +632,42 @@ class KoopmanNystromRegressor(KoopmanRegressor):
             kind, ls = kernel_spec(holder, d)
             inv_ls = torch.from_numpy(1.0 / ls).to(eng.tdev)
             Kzz = eng.kzz(Z, inv_ls, kind)
-            stacked = None
             t0 = tick()
-            for fi, (lo, hi) in enumerate(local):
-                eng.gram_begin(Z, inv_ls, kind, p, self.gram_chunk)
-                if hi > lo:
-                    eng.gram_update(Xd[lo:hi], Yd[lo:hi])
-                flat = eng.gram_finalize()["_flat"]
-                if stacked is None:
-                    stacked = torch.empty(n_splits, flat.numel(), dtype=torch.float64, device=eng.tdev)
-                stacked[fi].copy_(flat)
+
+            def gram_pass():
+                stacked = None
+                for fi, (lo, hi) in enumerate(local):
+                    eng.gram_begin(Z, inv_ls, kind, p, self.gram_chunk)
+                    if hi > lo:
+                        eng.gram_update(Xd[lo:hi], Yd[lo:hi])
+                    flat = eng.gram_finalize()["_flat"]
+                    if stacked is None:
+                        stacked = torch.empty(n_splits, flat.numel(), dtype=torch.float64, device=eng.tdev)
+                    stacked[fi].copy_(flat)
+                return stacked
+            stacked = self._agree(group, eng.tdev, gram_pass, "fit_cv_distributed: Gram pass")   # a failure on one rank raises on all
             sharding.allreduce_sum(stacked, group)                                  # per-fold Grams of ALL samples
             t1 = tick()
             Wall = torch.zeros(n_splits, nlam, d, m + p, dtype=torch.float64, device=eng.tdev)
             bad = torch.zeros(n_splits, nlam, dtype=torch.int32, device=eng.tdev)
             train = torch.empty_like(stacked[0])
-            last_fold = -1
-            for trank, fi, g0, g1 in tasks:
-                if trank != rank:
-                    continue
-                if fi != last_fold:
-                    train.zero_()
-                    for fj in range(n_splits):
-                        if fj != fi:
-                            eng.axpy(1.0, stacked[fj], train)
-                    last_fold = fi
-                n_train = n_total - (folds[fi][1] - folds[fi][0])
-                Wk, info = eng.cv_weights(eng.gram_views(train, m, d, p), Kzz, [g * n_train for g in gammas[g0:g1]], self.jitter)
-                Wall[fi, g0:g1].copy_(Wk)
-                bad[fi, g0:g1] = torch.as_tensor(info, dtype=torch.int32, device=eng.tdev)
+
+            def my_tasks():
+                last_fold = -1
+                for trank, fi, g0, g1 in tasks:
+                    if trank != rank:
+                        continue
+                    if fi != last_fold:
+                        train.zero_()
+                        for fj in range(n_splits):
+                            if fj != fi:
+                                eng.axpy(1.0, stacked[fj], train)
+                        last_fold = fi
+                    n_train = n_total - (folds[fi][1] - folds[fi][0])
+                    Wk, info = eng.cv_weights(eng.gram_views(train, m, d, p), Kzz, [g * n_train for g in gammas[g0:g1]], self.jitter)
+                    Wall[fi, g0:g1].copy_(Wk)
+                    bad[fi, g0:g1] = torch.as_tensor(info, dtype=torch.int32, device=eng.tdev)
+            self._agree(group, eng.tdev, my_tasks, "fit_cv_distributed: batched solves")
             sharding.allreduce_sum(Wall, group)                                     # every slice was written by exactly one rank
             sharding.allreduce_sum(bad, group)
             t2 = tick()
@@ -564,9 +740,9 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         d = X_aug.shape[1] - self.n_inputs
         dev = self._device_state(d)
         eng = dev["eng"]
-        W = dev.get("W")
-        if W is None or W.shape != self.weights.shape:
-            W = torch.from_numpy(np.ascontiguousarray(self.weights)).to(eng.tdev)
+        W = dev.get("W")                                  # set by fit; dropped when weights are assigned or the state is rebuilt
+        if W is None:
+            W = torch.from_numpy(np.ascontiguousarray(np.asarray(self.weights, dtype=np.float64))).to(eng.tdev)
             dev["W"] = W
         out = np.empty((N, d))
         step = max(1, int(2 ** 27 // max(self.m, 1)))
@@ -641,6 +817,50 @@ def _closed_loop(self, K, initial_states, references, num_steps):
 
 
 KoopmanNystromRegressor.closed_loop = _closed_loop
+
+
+def _lqr_closed_loop(self, K, initial_state, reference, num_steps, step):
+    """Closed loop on the TRUE system with one `lift` per step: `lqr_control` of benchmark_lqr_hjb.py:74-97 and
+    benchmark_lqr_classic.py:67-89 (u_i = K (phi_ref - phi(x_i)); x_{i+1} = step(x_i, u_i); phi recomputed from x_{i+1}).
+    `step(x (d,1), u (p,1)) -> x_next` is the caller's simulator (host code, e.g. DuffingOscillator.update_SOM).  The lift runs
+    on the device against the CACHED S^-1 (the reference re-runs scipy sqrtm inside every lift, 2000 times per seed); the state
+    goes up and the lifted state comes down through pinned buffers, a few tens of microseconds per step.
+    Returns (true states (d, num_steps+1), reconstructions C phi (d, num_steps), controls (p, num_steps))."""
+    import torch
+    x = np.asarray(initial_state, dtype=np.float64).reshape(-1, 1)
+    d = x.shape[0]
+    dev = self._device_state(d)
+    eng = dev["eng"]
+    K = np.asarray(K, dtype=np.float64)
+    C = np.asarray(self.C, dtype=np.float64)
+    m = dev["Z"].shape[0]
+    x_pin = torch.empty(1, d, dtype=torch.float64).pin_memory()
+    phi_pin = torch.empty(m, dtype=torch.float64).pin_memory()
+    x_dev = torch.empty(1, d, dtype=torch.float64, device=eng.tdev)
+    stream = torch.cuda.current_stream(eng.tdev)
+
+    def lift_point(col):
+        x_pin[0].copy_(torch.from_numpy(np.ascontiguousarray(col[:, 0])))
+        x_dev.copy_(x_pin, non_blocking=True)
+        phi = eng.lift(dev["Z"], dev["inv_ls"], dev["kind"], dev["Sinv"], x_dev, transposed=True)     # (1, m)
+        phi_pin.copy_(phi[0], non_blocking=True)
+        stream.synchronize()
+        return phi_pin.numpy().reshape(-1, 1).copy()
+    phi_ref = lift_point(np.asarray(reference, dtype=np.float64).reshape(-1, 1))
+    phi = lift_point(x)
+    xs = np.empty((d, num_steps + 1)); recon = np.empty((d, num_steps)); us = np.empty((K.shape[0], num_steps))
+    xs[:, 0] = x[:, 0]
+    for i in range(int(num_steps)):
+        u = K @ (phi_ref - phi)
+        us[:, i] = u[:, 0]
+        recon[:, i] = (C @ phi)[:, 0]
+        x = np.asarray(step(x, u), dtype=np.float64).reshape(-1, 1)
+        xs[:, i + 1] = x[:, 0]
+        phi = lift_point(x)
+    return xs, recon, us
+
+
+KoopmanNystromRegressor.lqr_closed_loop = _lqr_closed_loop
 
 
 # ----------------------------------------------------------------------------------------------

@@ -13,6 +13,9 @@ def shard_bounds(n_total: int, world: int, rank: int):
     return offset, n_local
 
 
+HEAD_COEFF = 64.0     # m^3-flop equivalents of the landmark-only stage (see head_samples); tools/multi_gpu_round.sh sweeps it
+
+
 def head_samples(m: int, d: int, p: int) -> int:
     """How many samples of fused lift+Gram work the landmark-only stage of a fit is worth (K_zz, Cholesky, 17 Newton-Schulz
     iterations of the symmetric square root, S and S^-1: ~56 m^3 flop on the row-major GEMM at ~82% of the DMMA rate, plus the
@@ -21,7 +24,7 @@ def head_samples(m: int, d: int, p: int) -> int:
     left the other ranks waiting ~17 ms for the head).  Overshooting is cheap (the surplus is spread over the other ranks),
     undershooting is paid in full."""
     per_sample = 4.0 * m * m + 6.0 * m * d + 4.0 * m * p
-    return int(64.0 * m ** 3 / per_sample * (0.90 / 0.82))
+    return int(HEAD_COEFF * m ** 3 / per_sample * (0.90 / 0.82))
 
 
 def balanced_bounds(n_total: int, world: int, rank: int, head: int = 0, head_rank: int = 0):
@@ -78,6 +81,29 @@ def allreduce_grams(flat, group=None):
     import torch.distributed as dist
     dist.all_reduce(flat, group=group)
     return flat
+
+
+# ---- column-sharded solve (nk_solve_abc_part) --------------------------------------------------------------------
+def solve_row_ranges(n_rows: int, world: int, rank: int):
+    """Rows of G^T ((m+p) x m) or C^T (m x d) that `rank` solves: equal slabs of ceil(n_rows / world) rows (the gather buffer
+    is world * slab rows, zero-padded at the end), the last ranks may get fewer or none.  Returns (slab, start, count)."""
+    slab = -(-int(n_rows) // int(world))
+    start = min(rank * slab, n_rows)
+    return slab, start, max(0, min(slab, n_rows - rank * slab))
+
+
+def gather_rows(all_buf, mine, group=None):
+    """Assembles the row slabs every rank computed into `all_buf` (world * slab rows; `mine` is this rank's slab, a view of
+    it).  NCCL: one all_gather; other backends (gloo in the tests): an all_reduce of the zero-filled buffer -- every row is
+    written by exactly one rank, so the sum is the concatenation."""
+    import torch.distributed as dist
+    if dist.get_world_size(group) == 1:
+        return all_buf
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(all_buf, mine.clone(), group=group)
+    else:
+        dist.all_reduce(all_buf, group=group)
+    return all_buf
 
 
 # ---- cross-validation sweep over several GPUs (SURVEY 8e, "CV sweep") ----------------------------------------------

@@ -12,6 +12,7 @@ ARGS = ["--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-sample", 
 
 def run(env_extra=None):
     env = dict(os.environ)
+    env.update({"NK_BENCH_REF_M": "48", "NK_BENCH_REF_N": "300,900"})          # the one unmodified-reference fit, shrunk
     env.update(env_extra or {})
     return subprocess.run([sys.executable, str(ROOT / "bench.py"), *ARGS], capture_output=True, text=True, cwd=ROOT, env=env, timeout=300)
 
@@ -31,6 +32,12 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == j["value"] and cb["sample"]
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert j["value"] > 0 and j["ms_per_step"] > 0
+    # the UNMODIFIED reference fit (baseline/_ref/regressors.py) is timed beside the port when it is on the box
+    um = cb["unmodified_reference"]
+    if (ROOT / "baseline" / "_ref" / "regressors.py").exists():
+        assert um["n"] == [300, 900] and len(um["fit_s"]) == 2 and um["m"] == 48 and "T0_s" in um and "r_samples_per_s" in um
+    else:
+        assert um is None
 
 
 def test_reference_arm_other_ranks_stay_silent():

@@ -148,3 +148,72 @@ def test_balanced_bounds_give_the_head_rank_a_shorter_block():
             assert abs((spans[hr][1] + head) - others[0]) <= 1      # equal total work
         else:
             assert spans == [sharding.shard_bounds(n, w, r) for r in range(w)]
+
+
+def test_solve_row_ranges_cover_every_column_once():
+    """Column-sharded solve (nk_solve_abc_part): every row of G^T / C^T belongs to exactly one rank, slabs are equal, the tail is padding."""
+    from nys_koop_lqr_b200 import sharding
+    for rows, world in ((4102, 8), (4102, 2), (106, 8), (7, 8), (3, 4), (1, 1), (4096, 3)):
+        seen = np.zeros(rows, dtype=int)
+        for r in range(world):
+            slab, start, count = sharding.solve_row_ranges(rows, world, r)
+            assert slab * world >= rows and 0 <= count <= slab and start + count <= rows
+            assert count == 0 or start == r * slab
+            seen[start:start + count] += 1
+        assert (seen == 1).all()
+
+
+def _solve_shard_worker(rank, world, port, out):
+    """The host side of the sharded solve with the oracle standing in for nk_solve_abc_part: each rank solves its columns,
+    gather_rows assembles G^T and C^T, and the result equals the one-process solve; a failure on one rank raises on both."""
+    from nys_koop_lqr_b200 import sharding
+    from nys_koop_lqr_b200.regressors import KoopmanNystromRegressor as K
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n, d, p, m = 700, 4, 2, 37
+        Xs, U, Y = O.synthetic(n, d, p, seed=8)
+        Z = Y[np.random.default_rng(0).choice(n, m, replace=False)]
+        ls = np.full(d, 2.5)
+        G = O.grams(Xs, Y, U, Z, O.RBF, ls)
+        Kzz = O.kernel_matrix(Z, Z, O.RBF, ls)
+        A, B, C, W = O.solve_abc(G, Kzz, 1e-2 * n)
+        GT_full, CT_full = np.hstack((A, B)).T, C.T
+        N1 = m + p
+        g_slab, g0, gc = sharding.solve_row_ranges(N1, world, rank)
+        c_slab, c0, cc = sharding.solve_row_ranges(m, world, rank)
+        GT_all = torch.zeros(world * g_slab, m, dtype=torch.float64)
+        CT_all = torch.zeros(world * c_slab, d, dtype=torch.float64)
+        GT_all[rank * g_slab:rank * g_slab + gc] = torch.from_numpy(GT_full[g0:g0 + gc])
+        CT_all[rank * c_slab:rank * c_slab + cc] = torch.from_numpy(CT_full[c0:c0 + cc])
+        sharding.gather_rows(GT_all, GT_all[rank * g_slab:(rank + 1) * g_slab])
+        sharding.gather_rows(CT_all, CT_all[rank * c_slab:(rank + 1) * c_slab])
+        ok = np.array_equal(GT_all[:N1].numpy(), GT_full) and np.array_equal(CT_all[:m].numpy(), CT_full)
+        ok = ok and float(GT_all[N1:].abs().sum()) == 0.0
+        # collective error agreement: rank 1 fails locally, BOTH ranks must raise (nobody is left waiting in a collective)
+        raised = False
+        try:
+            K._agree(None, "cpu", (lambda: 1 / 0) if rank == 1 else (lambda: 7), "stage")
+        except ZeroDivisionError:
+            raised = rank == 1
+        except Exception as exc:  # noqa: BLE001
+            raised = rank == 0 and "another rank" in str(exc)
+        assert K._agree(None, "cpu", lambda: rank, "stage") == rank
+        out.put((rank, bool(ok), bool(raised)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_solve_gather_and_error_agreement_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_solve_shard_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    for p_ in procs:
+        p_.join(timeout=120)
+        assert p_.exitcode == 0
+    got = sorted(out.get(timeout=5) for _ in range(2))
+    assert got == [(0, True, True), (1, True, True)]

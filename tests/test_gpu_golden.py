@@ -1,7 +1,9 @@
 """GPU: the drop-in estimator (host class -> C ABI -> sm_100a kernels) against the reference's golden outputs.
 
-Tolerance on A/B/C/weights: max(1e-9, 100 x reference self-floor) (fixtures carry the floor and cond(inner_term));
-lift/predict 1e-8; forecast RMSE 6 significant digits where the floor allows (SURVEY.md 8c protocol).
+Tolerance on A/B/C, the Riccati gain and predict: 1e-9 where cond(inner_term) < 1e7, else max(1e-9, 10 x the reference's own
+self-floor) (fixtures carry the floor -- the reference refitted with its samples permuted -- and cond(inner_term)); lift 1e-8;
+forecast RMSE 6 significant digits where the floor allows (SURVEY.md 8c protocol).  The ill-conditioned script configurations
+(cond 1e11 ... 1e14) are covered by tests/test_gpu_scripts.py with the distance-to-high-precision-truth protocol.
 """
 import pathlib
 import pickle
@@ -39,7 +41,7 @@ def test_estimator_matches_reference_golden(engine, path):
     fx = np.load(path)
     reg = fitted(fx)
     for key, got in (("A", reg.A), ("B", reg.B), ("C", reg.C)):
-        tol = 30 * max(1e-9, 100.0 * float(fx[f"floor_{key}"]))
+        tol = max(1e-9, 10.0 * float(fx[f"floor_{key}"]))
         if float(fx["cond_inner"]) < 1e7:
             tol = 1e-9       # the north-star bar where conditioning allows it
         err = O.relerr(got, fx[key])
@@ -47,7 +49,7 @@ def test_estimator_matches_reference_golden(engine, path):
         assert err <= tol, f"{key}: {err:.2e} > {tol:.1e} (cond {float(fx['cond_inner']):.1e}, floor {float(fx['floor_' + key]):.1e})"
     d = fx["Y"].shape[1]
     assert O.relerr(reg.lift(fx["Xq"][:, :d].T), fx["lift_q"]) <= 1e-8
-    werr = max(1e-8, 3000 * float(fx["floor_A"]))
+    werr = max(1e-8, 10.0 * (float(fx["floor_A"]) + float(fx["floor_C"])))
     assert O.relerr(reg.predict(fx["Xq"]), fx["predict_q"]) <= werr
     if "sim" in fx.files:
         T = fx["traj"].shape[1]
@@ -59,8 +61,8 @@ def test_estimator_matches_reference_golden(engine, path):
     if "K_lqr" in fx.files:
         Q = (1.0 if d != 192 else 0.005) * reg.C.T @ reg.C
         K, _ = O.dlqr(reg.A, reg.B, (Q + Q.T) / 2, np.eye(int(fx["n_inputs"])))     # DARE stays on the host (north star)
-        # Riccati gain: <=1e-9 where the reference itself reproduces it that well, else 100 x its own self-floor
-        assert O.relerr(K, fx["K_lqr"]) <= max(1e-9, 100.0 * float(fx["floor_K"]))
+        # Riccati gain: <=1e-9 where the reference itself reproduces it that well, else 10 x its own self-floor
+        assert O.relerr(K, fx["K_lqr"]) <= max(1e-9, 10.0 * float(fx["floor_K"])), (O.relerr(K, fx["K_lqr"]), float(fx["floor_K"]))
 
 
 def test_landmark_draw_refit_and_pickle(engine):
