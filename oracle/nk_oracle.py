@@ -61,11 +61,12 @@ def kernel_matrix(A_rows, B_rows, kind, length_scale):
 # --------------------------------------------------------------------------------------------
 # the seven data-sample Grams  (regressors.py:147,151,153,162,164)
 # --------------------------------------------------------------------------------------------
-def grams(Xs, Y, U, Z, kind, length_scale, chunk=8192, threads=1):
+def grams(Xs, Y, U, Z, kind, length_scale, chunk=8192, threads=1, Z_in=None):
     """Xs (n,d) states, Y (n,d) next states, U (n,p) controls, Z (m,d) landmarks.
 
     Returns dict: Gxx = Phi_x Phi_x' (m,m), Gyx = Phi_y Phi_x' (m,m), Gyy (m,m), Gxu = Phi_x U (m,p),
     Gyu (m,p), Guu (p,p), GYy = Y' Phi_y' (d,m); Phi_x = k(Z, Xs) (m,n), Phi_y = k(Z, Y).
+    Z_in: distinct input landmarks (regressors.py:133-134, 142): Phi_x = k(Z_in, Xs); default Z_in = Z.
     Chunked over samples so n*m never has to exist (the reference materialises it; the sums are the same).
     threads > 1: the kernel lifts of a chunk (scipy cdist releases the GIL) are computed by a thread pool over column
     strips -- same arithmetic per entry, so the result is bit-identical to threads=1; only the wall time changes (the
@@ -80,16 +81,17 @@ def grams(Xs, Y, U, Z, kind, length_scale, chunk=8192, threads=1):
         from concurrent.futures import ThreadPoolExecutor
         pool = ThreadPoolExecutor(int(threads))
 
-    def lifted(rows):
+    def lifted(rows, Zc=None):
+        Zc = Z if Zc is None else Zc
         if pool is None or rows.shape[0] < 2 * threads:
-            return kernel_matrix(Z, rows, kind, length_scale)
+            return kernel_matrix(Zc, rows, kind, length_scale)
         cuts = np.linspace(0, rows.shape[0], int(threads) + 1).astype(int)
-        parts = list(pool.map(lambda i: kernel_matrix(Z, rows[cuts[i]:cuts[i + 1]], kind, length_scale), range(int(threads))))
+        parts = list(pool.map(lambda i: kernel_matrix(Zc, rows[cuts[i]:cuts[i + 1]], kind, length_scale), range(int(threads))))
         return np.hstack(parts)
     try:
         for s in range(0, n, chunk):
             e = min(n, s + chunk)
-            Px = lifted(Xs[s:e])
+            Px = lifted(Xs[s:e], Z_in)
             Py = lifted(Y[s:e])
             Uc, Yc = U[s:e], Y[s:e]
             G["Gxx"] += Px @ Px.T
@@ -125,14 +127,17 @@ def landmark_matrices(Z, kind, length_scale, sqrt="eigh"):
 # --------------------------------------------------------------------------------------------
 # dense stage: Grams -> (A, B, C, W)   (regressors.py:147-169)
 # --------------------------------------------------------------------------------------------
-def solve_abc(G, Kzz, gamma_n, solver="chol"):
+def solve_abc(G, Kzz, gamma_n, solver="chol", Kzz_in=None, Kio=None):
     """solver='reference': scipy sqrtm / solve(assume_a='her') / lstsq in the reference's call order.
-    solver='chol': eigh root + Cholesky solves (what the sm_100a dense stage computes)."""
+    solver='chol': eigh root + Cholesky solves (what the sm_100a dense stage computes).
+    Kzz_in = k(Z_in, Z_in), Kio = k(Z_in, Z_out) (regressors.py:143-144) when the input landmarks differ; default both = Kzz."""
     m = Kzz.shape[0]
     p = G["Guu"].shape[0]
     Kmm = Kzz + JITTER * np.eye(m)
+    Kmm_in = Kmm if Kzz_in is None else Kzz_in + JITTER * np.eye(m)
+    Kio = Kzz if Kio is None else Kio
     inner = np.empty((m + p, m + p))
-    inner[:m, :m] = G["Gxx"] + gamma_n * Kmm
+    inner[:m, :m] = G["Gxx"] + gamma_n * Kmm_in
     inner[:m, m:] = G["Gxu"]
     inner[m:, :m] = G["Gxu"].T
     inner[m:, m:] = G["Guu"] + gamma_n * np.eye(p)
@@ -140,7 +145,7 @@ def solve_abc(G, Kzz, gamma_n, solver="chol"):
     inner_rec = gamma_n * Kmm + G["Gyy"]      # (:162)
     if solver == "reference":
         S = scipy.linalg.sqrtm(Kmm).real
-        right = scipy.linalg.block_diag(scipy.linalg.solve(S, Kzz.T, assume_a="her").T, np.eye(p))
+        right = scipy.linalg.block_diag(scipy.linalg.solve(S, Kio.T, assume_a="her").T, np.eye(p))
         left = scipy.linalg.solve(S, cross, assume_a="her")
         sol = scipy.linalg.lstsq(inner, right)[0]
         Gls = left @ sol
@@ -150,7 +155,7 @@ def solve_abc(G, Kzz, gamma_n, solver="chol"):
         w, V = np.linalg.eigh(Kmm)
         S = (V * np.sqrt(w)) @ V.T
         Sinv = (V / np.sqrt(w)) @ V.T
-        right = scipy.linalg.block_diag(Kzz @ Sinv, np.eye(p))
+        right = scipy.linalg.block_diag(Kio @ Sinv, np.eye(p))
         left = Sinv @ cross
         sol = scipy.linalg.cho_solve(scipy.linalg.cho_factor(inner, lower=True), right)
         Gls = left @ sol
@@ -169,17 +174,20 @@ def draw_landmarks(Y, m):
     return Y[idx]
 
 
-def fit(X_aug, Y, n_inputs, kind, length_scale, gamma, m=None, Z=None, solver="chol"):
-    """X_aug (n, d+p) with the p controls LAST (regressors.py:122-126), Y (n,d). Returns dict."""
+def fit(X_aug, Y, n_inputs, kind, length_scale, gamma, m=None, Z=None, solver="chol", Z_in=None):
+    """X_aug (n, d+p) with the p controls LAST (regressors.py:122-126), Y (n,d). Returns dict.  Z_in: distinct input landmarks."""
     X_aug = np.asarray(X_aug, dtype=np.float64)
     Y = np.asarray(Y, dtype=np.float64)
     n = X_aug.shape[0]
     d = X_aug.shape[1] - n_inputs
     if Z is None:
         Z = draw_landmarks(Y, m)
-    G = grams(X_aug[:, :d], Y, X_aug[:, d:], Z, kind, length_scale)
+    G = grams(X_aug[:, :d], Y, X_aug[:, d:], Z, kind, length_scale, Z_in=Z_in)
     Kzz = kernel_matrix(Z, Z, kind, length_scale)
-    A, B, C, W = solve_abc(G, Kzz, gamma * n, solver=solver)
+    Kzz_in = Kio = None
+    if Z_in is not None:
+        Kzz_in, Kio = kernel_matrix(Z_in, Z_in, kind, length_scale), kernel_matrix(Z_in, Z, kind, length_scale)
+    A, B, C, W = solve_abc(G, Kzz, gamma * n, solver=solver, Kzz_in=Kzz_in, Kio=Kio)
     return dict(A=A, B=B, C=C, W=W, Z=Z, G=G, Kzz=Kzz)
 
 

@@ -34,30 +34,36 @@ def reference_rollout(reg, true_traj, controls):
     return sim
 
 
-def run_case(name, X, Y, n_inputs, kernel, kind, ls, gamma, m, seed, Xq, traj=None, ctrl=None, q_scale=1.0):
-    """X (n, d+p), Y (n, d) rows."""
+def run_case(name, X, Y, n_inputs, kernel, kind, ls, gamma, m, seed, Xq, traj=None, ctrl=None, q_scale=1.0, distinct_input=False):
+    """X (n, d+p), Y (n, d) rows.  distinct_input: inject input landmarks drawn from the CURRENT states (regressors.py:133-134
+    only aliases the output landmarks when nystrom_centers_input is unset)."""
     n = X.shape[0]
     np.random.seed(seed)
     idx = np.random.choice(np.arange(0, n), size=m, replace=False)       # regressors.py:130
     Zc = Y.T[:, idx]
+    Zin = Zc
+    if distinct_input:
+        Zin = np.ascontiguousarray(X[np.random.choice(np.arange(0, n), size=m, replace=False), :Y.shape[1]].T)
     reg = ref.KoopmanNystromRegressor(n_inputs, kernel=kernel, gamma=gamma, m=m)
     reg.nystrom_centers_output = Zc
-    reg.nystrom_centers_input = Zc
+    reg.nystrom_centers_input = Zin
     reg.fit(X, Y)
     # self-floor: same landmarks, permuted samples
     perm = np.random.default_rng(1).permutation(n)
     reg2 = ref.KoopmanNystromRegressor(n_inputs, kernel=kernel, gamma=gamma, m=m)
     reg2.nystrom_centers_output = Zc
-    reg2.nystrom_centers_input = Zc
+    reg2.nystrom_centers_input = Zin
     reg2.fit(X[perm], Y[perm])
     floor = dict(A=O.relerr(reg2.A, reg.A), B=O.relerr(reg2.B, reg.B), C=O.relerr(reg2.C, reg.C))
     d = Y.shape[1]
     out = dict(X=X, Y=Y, n_inputs=n_inputs, kind=kind, ls=np.asarray(ls, dtype=float), gamma=gamma, m=m, seed=seed, Z=Zc,
                A=reg.A, B=reg.B, C=reg.C, W=reg.weights, floor_A=floor["A"], floor_B=floor["B"], floor_C=floor["C"],
                Xq=Xq, lift_q=reg.lift(Xq[:, :d].T), predict_q=reg.predict(Xq))
+    if distinct_input:
+        out["Z_in"] = Zin
     # conditioning of the first system (regressors.py:151)
-    G = O.grams(X[:, :d], Y, X[:, d:], Zc.T, kind, ls)
-    Kzz = O.kernel_matrix(Zc.T, Zc.T, kind, ls)
+    G = O.grams(X[:, :d], Y, X[:, d:], Zin.T, kind, ls)
+    Kzz = O.kernel_matrix(Zin.T, Zin.T, kind, ls)
     inner = np.block([[G["Gxx"] + gamma * n * (Kzz + 1e-6 * np.eye(m)), G["Gxu"]], [G["Gxu"].T, G["Guu"] + gamma * n * np.eye(n_inputs)]])
     out["cond_inner"] = np.linalg.cond(inner)
     if traj is not None:
@@ -82,6 +88,7 @@ def run_case(name, X, Y, n_inputs, kernel, kind, ls, gamma, m, seed, Xq, traj=No
 
 def main():
     rng = np.random.default_rng(0)
+    only = sys.argv[1:]
     # ---- synthetic (SURVEY 8d family), small ----
     Xs, U, Y = O.synthetic(1500, d=12, p=2, seed=3)
     X = np.hstack((Xs, U))
@@ -89,6 +96,11 @@ def main():
              X[:50], traj=None)
     run_case("synthetic_rbf_g1e-2", X, Y, 2, ref.ThreeDimensionalKernel(3.0, 4.0, 5.0, 12), O.RBF, np.resize([3.0, 4.0, 5.0], 12), 1e-2, 64, 0,
              X[:50], traj=None)
+    # distinct input / output landmark sets (a caller may inject nystrom_centers_input, regressors.py:133-134)
+    run_case("synthetic_rbf_distinct_centers", X, Y, 2, ref.ThreeDimensionalKernel(3.0, 4.0, 5.0, 12), O.RBF, np.resize([3.0, 4.0, 5.0], 12), 1e-2, 64,
+             0, X[:50], traj=None, distinct_input=True)
+    if only == ["distinct"]:
+        return
     # ---- Duffing (benchmark_lqr_classic.py:174-178 data), every 20th sample; Matern-5/2 l=[1,1], gamma=1e-6 (G6/G1) ----
     dx = np.hstack((np.loadtxt(REF / "duffing/duffing_x_forced.csv", delimiter=","), np.loadtxt(REF / "duffing/duffing_x_unforced.csv", delimiter=",")))
     du = np.hstack((np.loadtxt(REF / "duffing/duffing_u_forced.csv", delimiter=",").reshape(1, -1), np.zeros((1, np.loadtxt(REF / "duffing/duffing_x_unforced.csv", delimiter=",").shape[1]))))
