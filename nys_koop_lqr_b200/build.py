@@ -12,7 +12,7 @@ import subprocess
 HERE = pathlib.Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libnkb200.so"
-SOURCES = ["nk_api.cu", "nk_gram.cu", "nk_dense.cu", "nk_rollout.cu", "nk_cv.cu", "nk_pgemm.cu"]
+SOURCES = ["nk_api.cu", "nk_gram.cu", "nk_dense.cu", "nk_rollout.cu", "nk_cv.cu", "nk_pgemm.cu", "nk_tgemm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"] + os.environ.get("NK_EXTRA_NVCC_FLAGS", "").split()

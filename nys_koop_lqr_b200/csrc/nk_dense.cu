@@ -209,6 +209,7 @@ void gemm_nt_batched(nk_handle *h, int batch, int M, int N, int K, double alpha,
                      const double *B, long long ldb, long long sB, double beta, double *C, long long ldc, long long sC, double diag,
                      int flags, double *Ct, long long ldct, long long sCt, cudaStream_t stream, int epi_kind) {
     if (M <= 0 || N <= 0 || batch <= 0) return;
+    if (tgemm_try(h, batch, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, diag, flags, Ct, ldct, sCt, stream, epi_kind)) return;
     static unsigned long long configured = 0;
     if (first_use_on_device(configured)) {
         cudaFuncSetAttribute(gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
@@ -828,8 +829,8 @@ int nk_solve_abc_part(nk_handle *h, int m, int p, int d, double gamma_n, double 
     double *inner = dense_scratch(h, 0, (size_t)N1 * ld1, &rc); if (rc) return rc;
     double *Lt = dense_scratch(h, 1, (size_t)N1 * ld1, &rc); if (rc) return rc;
     double *Rt = dense_scratch(h, 2, (size_t)(g_rows > c_rows ? g_rows : c_rows) * ld1 + 2, &rc); if (rc) return rc;
-    double *cross = dense_scratch(h, 3, (size_t)m * ld1, &rc); if (rc) return rc;
-    double *T1 = dense_scratch(h, 4, (size_t)(g_rows > 0 ? g_rows : 1) * ldm, &rc); if (rc) return rc;
+    double *crossT = dense_scratch(h, 3, (size_t)N1 * ldm, &rc); if (rc) return rc;
+    double *left = dense_scratch(h, 4, (size_t)m * ld1, &rc); if (rc) return rc;
     double *dinv = dense_scratch(h, 8, (size_t)nblk1 * kDB * kDB, &rc); if (rc) return rc;
     double *dinvT = dense_scratch(h, 9, (size_t)nblk1 * kDB * kDB, &rc); if (rc) return rc;
     if ((rc = ensure(h, h->dinfo, 64)) != NK_OK) return rc;
@@ -860,13 +861,16 @@ int nk_solve_abc_part(nk_handle *h, int m, int p, int d, double gamma_n, double 
         h->launches++;
         trsm_fwd_t(h, N1, g_rows, inner, ld1, dinv, Rt, ld1, stream);                         // sol^T rows = right^T rows inner^-1
         trsm_bwd_t(h, N1, g_rows, Lt, ld1, dinvT, Rt, ld1, stream);
-        // cross = [Gyx | Gyu]  (K_mn_out K_mn_in^T, regressors.py:153), concatenated so that its rows are contraction-contiguous
-        NK_CUDA(h, cudaMemcpy2DAsync(cross, (size_t)ld1 * 8, G->Gyx, (size_t)G->ld_gyx * 8, (size_t)m * 8, m, cudaMemcpyDeviceToDevice, stream));
-        if (p) NK_CUDA(h, cudaMemcpy2DAsync(cross + m, (size_t)ld1 * 8, G->Gyu, (size_t)G->ld_gyu * 8, (size_t)p * 8, m, cudaMemcpyDeviceToDevice, stream));
-        if (ld1 > N1) NK_CUDA(h, cudaMemset2DAsync(cross + N1, (size_t)ld1 * 8, 0, (size_t)(ld1 - N1) * 8, m, stream));
-        // G^T rows = (sol^T rows cross^T) S^-1      [G = S^-1 (cross sol)]
-        gemm_nt(h, g_rows, m, N1, 1.0, Rt, ld1, cross, ld1, 0.0, T1, ldm, 0.0, 0, nullptr, 0, stream);
-        gemm_nt(h, g_rows, m, m, 1.0, T1, ldm, L->Sinv, L->ld_sinv, 0.0, GT, ld_gt, 0.0, 0, nullptr, 0, stream);
+        // left = S^-1 [Gyx | Gyu]  (regressors.py:153), formed BEFORE the product with sol, as the reference does: cross * sol
+        // cancels by a factor cond(inner_term), and applying S^-1 to that product afterwards would amplify its rounding errors by
+        // ||S^-1|| (measured on the hjb configuration, cond(K_mm) 7e7: 350 x further from a high-precision solve).  S^-1 cross
+        // itself is benign: the columns of cross lie in the range of the kernel matrix.  Every device forms all of `left`
+        // (2 m^2 (m+p) flop, 4.5 ms at m = 4096); only the product with its own columns of sol is sharded.
+        transpose(h, m, m, G->Gyx, G->ld_gyx, crossT, ldm, stream);                               // cross^T = [Gyx | Gyu]^T
+        if (p) transpose(h, m, p, G->Gyu, G->ld_gyu, crossT + (long long)m * ldm, ldm, stream);
+        gemm_nt(h, m, N1, m, 1.0, L->Sinv, L->ld_sinv, crossT, ldm, 0.0, left, ld1, 0.0, 0, nullptr, 0, stream);   // left = S^-1 cross
+        // G^T rows = sol^T rows * left^T      [G = left sol]
+        gemm_nt(h, g_rows, m, N1, 1.0, Rt, ld1, left, ld1, 0.0, GT, ld_gt, 0.0, 0, nullptr, 0, stream);
     }
 
     // ---- reconstruction: C = GYy (gn Kmm + Gyy)^-1 S   (regressors.py:162-166), rows of C^T = columns of C ----

@@ -23,6 +23,12 @@ void gemm_nt_batched(nk_handle *h, int batch, int M, int N, int K, double alpha,
                      const double *B, long long ldb, long long sB, double beta, double *C, long long ldc, long long sC, double diag,
                      int flags, double *Ct, long long ldct, long long sCt, cudaStream_t stream, int epi_kind = -1);
 
+// TMA-fed persistent variant (nk_tgemm.cu): launches the product and returns true when the operands qualify (16-byte aligned,
+// even strides, enough tiles to fill the GPU); gemm_nt_batched tries it first.
+bool tgemm_try(nk_handle *h, int batch, int M, int N, int K, double alpha, const double *A, long long lda, long long sA, const double *B,
+               long long ldb, long long sB, double beta, double *C, long long ldc, long long sC, double diag, int flags, double *Ct,
+               long long ldct, long long sCt, cudaStream_t stream, int epi_kind);
+
 void transpose_batched(nk_handle *h, int batch, int rows, int cols, const double *src, long long lds, long long ss, double *dst,
                        long long ldd, long long sd, cudaStream_t stream);
 void transpose(nk_handle *h, int rows, int cols, const double *src, long long lds, double *dst, long long ldd, cudaStream_t stream);

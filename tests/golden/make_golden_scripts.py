@@ -10,8 +10,9 @@ Each fixture holds: the landmarks of the reference's RNG call, the reference's A
 samples permuted), the Riccati gain (scipy DARE as the control.dlqr stand-in) and its floor, cond(inner_term), the open-loop
 forecast RMSE of validate_dyn_sys, the script's closed loop (hjb / classic: lqr_control on the true RK system with a lift per
 step; cloth: the lifted-model loop), and -- the SURVEY 8c protocol for the ill-conditioned configurations -- A from a
-HIGH-PRECISION solve of the same float64 system (Cholesky + iterative refinement with long-double residuals), with the
-distances of the reference (lstsq / gelsd) and of plain float64 Cholesky to it.
+HIGH-PRECISION evaluation of the same formulas on the same float64 Grams (square root from a 50-digit eigen-decomposition,
+solves refined with long-double residuals, long-double products), with the distances of the reference (sqrtm / lstsq) and of
+plain float64 eigh + Cholesky to it.
 
 Run:  python tests/golden/make_golden_scripts.py      (needs /root/reference; the fixtures are committed)
 """
@@ -31,27 +32,52 @@ from oracle import nk_oracle as O          # noqa: E402
 OUT = HERE / "scripts"
 
 
+def exact_sqrt_pair(Kmm, digits=50):
+    """S = K_mm^(1/2) and S^-1 from a 50-digit symmetric eigen-decomposition (mpmath), rounded to long double.  float64 eigh /
+    sqrtm / polar roots all carry ~eps * cond(K_mm) relative error in S^-1 (1e-8 on the Matern configurations), which the product
+    S^-1 [Gyx|Gyu] inner^-1 ... amplifies ~100 x; a "truth" must not share that error with any of the candidates."""
+    import mpmath as mp
+    mp.mp.dps = digits
+    m = Kmm.shape[0]
+    E, Q = mp.eigsy(mp.matrix(Kmm.tolist()))
+    ld = lambda M: np.array([[np.longdouble(mp.nstr(M[i, j], 25)) for j in range(M.cols)] for i in range(M.rows)], dtype=np.longdouble)
+    Ql = ld(Q)
+    w = np.array([np.longdouble(mp.nstr(E[i], 25)) for i in range(m)], dtype=np.longdouble)
+    return (Ql * np.sqrt(w)) @ Ql.T, (Ql / np.sqrt(w)) @ Ql.T
+
+
 def hp_truth(G, Kzz, gamma_n, refinements=60):
-    """[A|B] and C from the SAME float64 Grams, the two solves refined with long-double residuals (~cond * 5e-20 accurate)."""
+    """[A|B] and C from the SAME float64 Grams and kernel matrix, everything downstream in extended precision: S, S^-1 from a
+    50-digit eigen-decomposition, the two solves by Cholesky + iterative refinement with long-double residuals and a long-double
+    solution, the products in long double.  `*_chol`: the same formulas in plain float64 with an eigh root (the CPU statement of
+    what the GPU dense stage computes)."""
     m, p = Kzz.shape[0], G["Guu"].shape[0]
+    L = np.longdouble
     Kmm = Kzz + 1e-6 * np.eye(m)
+    S_x, Sinv_x = exact_sqrt_pair(Kmm)
     w, V = np.linalg.eigh(Kmm)
     S, Sinv = (V * np.sqrt(w)) @ V.T, (V / np.sqrt(w)) @ V.T
     inner = np.block([[G["Gxx"] + gamma_n * Kmm, G["Gxu"]], [G["Gxu"].T, G["Guu"] + gamma_n * np.eye(p)]])
-    right = scipy.linalg.block_diag(Kzz @ Sinv, np.eye(p))
-    left = Sinv @ np.hstack((G["Gyx"], G["Gyu"]))
+    cross = np.hstack((G["Gyx"], G["Gyu"]))
 
-    def refined(M, R):
+    def refined(M, R_exact):
         cf = scipy.linalg.cho_factor(M, lower=True)
-        x0 = scipy.linalg.cho_solve(cf, R)
-        x = x0.copy()
-        ML, RL = M.astype(np.longdouble), R.astype(np.longdouble)
+        x = scipy.linalg.cho_solve(cf, R_exact.astype(np.float64)).astype(L)
+        ML = M.astype(L)
         for _ in range(refinements):
-            x = x + scipy.linalg.cho_solve(cf, (RL - ML @ x.astype(np.longdouble)).astype(np.float64))
-        return x0, x
-    sol0, sol = refined(inner, right)
-    rec0, rec = refined(gamma_n * Kmm + G["Gyy"], S)
-    return dict(G_hp=left @ sol, G_chol=left @ sol0, C_hp=G["GYy"] @ rec, C_chol=G["GYy"] @ rec0, cond_inner=np.linalg.cond(inner))
+            x = x + scipy.linalg.cho_solve(cf, (R_exact - ML @ x).astype(np.float64)).astype(L)
+        return x
+    right_x = np.zeros((m + p, m + p), dtype=L)
+    right_x[:m, :m] = Kzz.astype(L) @ Sinv_x
+    right_x[m:, m:] = np.eye(p)
+    G_hp = ((Sinv_x @ cross.astype(L)) @ refined(inner, right_x)).astype(np.float64)
+    C_hp = (G["GYy"].astype(L) @ refined(gamma_n * Kmm + G["Gyy"], S_x)).astype(np.float64)
+    # plain float64 statement (eigh root, Cholesky, reference association order)
+    right = scipy.linalg.block_diag(Kzz @ Sinv, np.eye(p))
+    G_chol = (Sinv @ cross) @ scipy.linalg.cho_solve(scipy.linalg.cho_factor(inner, lower=True), right)
+    C_chol = G["GYy"] @ scipy.linalg.cho_solve(scipy.linalg.cho_factor(gamma_n * Kmm + G["Gyy"], lower=True), S)
+    return dict(G_hp=G_hp, G_chol=G_chol, C_hp=C_hp, C_chol=C_chol, cond_inner=np.linalg.cond(inner),
+                sinv_eigh_vs_exact=O.relerr(Sinv, Sinv_x.astype(np.float64)), cond_kmm=float(w[-1] / w[0]))
 
 
 def fit_reference(mod, make, X, Y, seed):
@@ -84,14 +110,16 @@ def common(reg, reg2, X, Y, kind, ls, gamma, qscale, mod):
                K_lqr=K, floor_K=O.relerr(K2, K), cond_inner=hp["cond_inner"],
                A_hp=hp["G_hp"][:, :m], B_hp=hp["G_hp"][:, m:], C_hp=hp["C_hp"],
                ref_vs_hp_A=O.relerr(reg.A, hp["G_hp"][:, :m]), chol_vs_hp_A=O.relerr(hp["G_chol"][:, :m], hp["G_hp"][:, :m]),
-               ref_vs_hp_C=O.relerr(reg.C, hp["C_hp"]), chol_vs_hp_C=O.relerr(hp["C_chol"], hp["C_hp"]))
+               ref_vs_hp_C=O.relerr(reg.C, hp["C_hp"]), chol_vs_hp_C=O.relerr(hp["C_chol"], hp["C_hp"]),
+               sinv_eigh_vs_exact=hp["sinv_eigh_vs_exact"], cond_kmm=hp["cond_kmm"])
     return out
 
 
 def describe(name, out):
     print(f"{name}: m={int(out['m'])} cond(inner)={float(out['cond_inner']):.1e} floor A/B/C {float(out['floor_A']):.1e}/{float(out['floor_B']):.1e}/"
           f"{float(out['floor_C']):.1e} K {float(out['floor_K']):.1e}; vs HP truth: reference A {float(out['ref_vs_hp_A']):.1e} C {float(out['ref_vs_hp_C']):.1e}, "
-          f"float64 Cholesky A {float(out['chol_vs_hp_A']):.1e} C {float(out['chol_vs_hp_C']):.1e}", flush=True)
+          f"float64 Cholesky A {float(out['chol_vs_hp_A']):.1e} C {float(out['chol_vs_hp_C']):.1e}; cond(K_mm) {float(out['cond_kmm']):.1e}, "
+          f"eigh S^-1 vs exact {float(out['sinv_eigh_vs_exact']):.1e}", flush=True)
 
 
 def make_hjb():
