@@ -339,6 +339,8 @@ def run_gpu_arm(args):
         reg.nystrom_centers_output = centers.copy()               # fresh object: nothing cached from earlier steps
         if distributed:
             reg.fit_distributed(Xin, Yin)
+            if rank == 0:                                          # results are read on the host once per node: rank 0
+                _ = (reg.A, reg.B, reg.C, reg.weights)             # downloads them INSIDE the timed region; the other ranks keep theirs on the device
         else:
             reg.fit(Xin, Yin)
         return reg
@@ -410,6 +412,20 @@ def run_gpu_arm(args):
                "d2h_bytes_per_step": int(out_bytes), "ms_per_step": ms_e2e, "steps": e2e_steps,
                "note": "per-rank bytes; samples streamed from pinned host memory in 262144-row blocks on a copy stream overlapped with the fused kernel"}
 
+    # ---- BASELINE.json configs[4] at reduced size, untimed by the headline: a driver-visible record of the CV sweep + rollout ----
+    extra = None
+    if world == 1 and not args.no_config5:
+        try:
+            del X, Y, Xh, Yh
+            torch.cuda.empty_cache()
+            import bench_cv
+            c5 = bench_cv.run(bench_cv.parse(["--n", "200000", "--m", "8192", "--kernels", "2", "--gammas", "16", "--traj", "10000"]), standalone=False)
+            extra = {"config5_small": {k: c5[k] for k in ("config", "cv_seconds", "phase_seconds", "refit_seconds", "cv_fits_per_s", "gram_pass",
+                                                          "batched_solves", "scoring", "rollout", "best")},
+                     "note": "BASELINE.json configs[4] (16 x 16 sweep at m=8192, n=2e6, 1e5 trajectories) scaled to 2 lengthscales x 16 gamma, n=2e5, "
+                             "1e4 trajectories so that it fits the default run; full size: python bench_cv.py (profiles/)"}
+        except Exception as exc:  # noqa: BLE001
+            extra = {"config5_small": None, "error": repr(exc)}
     if rank == 0:
         cpu = None
         if not args.no_cpu and world == 1:           # the CPU baseline is reported at N=1 only
@@ -442,7 +458,7 @@ def run_gpu_arm(args):
                          "peak_nominal": 40.0, "frac_nominal": (achieved / 40.0) if achieved else None,
                          "nominal_note": "NVIDIA's B200 FP64 tensor figure (40 TFLOP/s); the DMMA issue rate measured on this pool is 37.1",
                          "gpu_launches_note": "gpu_launches = kernels of libnkb200.so launched per step (one fit), counted by the handle"},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(round(launches / max(args.steps, 1))), "clocks": clocks, "parity": parity,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(round(launches / max(args.steps, 1))), "clocks": clocks, "parity": parity, "extra": extra,
             "model_check": {"A_shape": list(reg.A.shape), "A_fro": float(np.linalg.norm(reg.A)), "finite": bool(np.isfinite(reg.A).all() and np.isfinite(reg.C).all())},
         }
         emit(line)
@@ -468,6 +484,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ref-fit", action="store_true", help="reference arm: skip the one unmodified baseline/_ref fit")
+    ap.add_argument("--no-config5", action="store_true", help="skip the reduced configs[4] (CV sweep + rollout) side measurement")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity check on a numpy prefix before the timed region")
     ap.add_argument("--parity-samples", type=int, default=8192)
     args = ap.parse_args()

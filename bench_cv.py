@@ -47,7 +47,7 @@ def emit(line):
     out.flush()
 
 
-def main():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--samples", "--n", dest="n", type=int, default=2_000_000)
     ap.add_argument("--landmarks", "--m", dest="m", type=int, default=8192)
@@ -58,9 +58,20 @@ def main():
     ap.add_argument("--folds", type=int, default=5)
     ap.add_argument("--traj", type=int, default=100_000)
     ap.add_argument("--T", type=int, default=101)
-    args = ap.parse_args()
-    protect_stdout()
+    return ap.parse_args(argv)
 
+
+def main():
+    args = parse()
+    protect_stdout()
+    line = run(args)
+    if line is not None:
+        emit(line)
+
+
+def run(args, standalone=True):
+    """One pass of configs[4] at the sizes in `args`; returns the result dict on rank 0 (None elsewhere).  `standalone=False`:
+    called from bench.py inside an already initialised single-GPU process (no process-group handling)."""
     import torch
     import regressors as R
     from nys_koop_lqr_b200.engine import Engine
@@ -73,6 +84,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    if not standalone:
+        world, rank = 1, 0
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")   # lands on stderr (protect_stdout)
         dist.init_process_group("nccl", device_id=dev)
@@ -167,11 +180,11 @@ def main():
                  "score": reg.best_score_, "nan_candidates": int(np.isnan(res["mean_test_score"]).sum())},
         "dtype": "f64", "data": "synthetic", "n_gpus": world,
     }
-    if rank == 0:
-        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    eng.release_scratch()
+    return line if rank == 0 else None
 
 
 if __name__ == "__main__":

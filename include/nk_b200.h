@@ -59,6 +59,16 @@ int nk_gram_finalize(nk_handle *h, double *Gxx, long long ld_gxx, double *Gyx, l
  * NK_E_STATE by the next SYNCHRONISING call (nk_solve_abc / nk_solve_abc_part / nk_cv_weights) or by nk_gram_status, which
  * synchronises `stream` and returns NK_OK / NK_E_STATE. */
 int nk_gram_status(nk_handle *h, void *stream);
+/* ---- the one data-path collective of the sample-sharded fit: float64 sum of the packed Grams over the devices.
+ * `packed` is this device's buffer of `count` doubles (any layout, typically [Gxx|Gyx|Gyy|Gxu|Gyu|Guu|GYy] as one allocation),
+ * reduced IN PLACE on `stream` with ncclAllReduce(..., ncclDouble, ncclSum, comm, stream).  `nccl_comm` is the caller's
+ * ncclComm_t for this device (the host owns communicator set-up: ncclCommInitAll / ncclCommInitRank, or torch.distributed's).
+ * The library does not link NCCL: the symbol is taken from the NCCL already loaded in the process (dlsym), NK_E_STATE if none is.
+ * In a single process driving several devices wrap the per-device calls in ncclGroupStart / ncclGroupEnd as usual.
+ * With this entry point a host without Python shards a fit: per device nk_gram_begin / update / finalize on its sample block,
+ * nk_allreduce_grams, then nk_solve_abc (or nk_solve_abc_part + an all-gather) -- tests/test_c_two_devices.py does exactly that. */
+int nk_allreduce_grams(nk_handle *h, void *nccl_comm, double *packed, long long count, void *stream);
+
 /* Introspection, HOST ONLY (no device needed): the work plan nk_gram_begin builds for these sizes on a GPU with sm_count SMs.
  * summary[12] = {chunk, MP, KLS, EP, psi_rows, nblk, ntiles, n_pack, n_lift, n_gram, period_len, nslots};  items (may be NULL)
  * receives up to items_cap entries of ONE period of the global work order, 4 ints each {type (0 pack, 1 lift, 2 Gram tile), a, b, c}

@@ -43,6 +43,7 @@ _SIGNATURES = {
     "nk_gram_begin": ([C.c_void_p, _c_dp, _ll, _i, _i, _i, _c_dp, _i, _i, C.c_void_p], _i),
     "nk_gram_begin_io": ([C.c_void_p, _c_dp, _ll, _c_dp, _ll, _i, _i, _i, _c_dp, _i, _i, C.c_void_p], _i),
     "nk_gram_status": ([C.c_void_p, C.c_void_p], _i),
+    "nk_allreduce_grams": ([C.c_void_p, C.c_void_p, _c_dp, _ll, C.c_void_p], _i),
     "nk_gram_update": ([C.c_void_p, _c_dp, _ll, _c_dp, _ll, _ll, C.c_void_p], _i),
     "nk_gram_finalize": ([C.c_void_p] + [_c_dp, _ll] * 7 + [_i, C.c_void_p], _i),
     "nk_gram_plan": ([_i, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), _i], _i),

@@ -50,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
             print(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [NVCC, "-shared", "-o", str(LIB), *objs, "-lcudart"]
+    cmd = [NVCC, "-shared", "-o", str(LIB), *objs, "-lcudart", "-ldl"]
     subprocess.run(cmd, check=True)
     stamp_file.write_text(stamp)
     return LIB

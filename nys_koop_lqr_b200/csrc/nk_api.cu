@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
+#include <dlfcn.h>
 #include "nk_handle.cuh"
 
 namespace nk {
@@ -362,6 +363,33 @@ int nk_gram_finalize(nk_handle *h, double *Gxx, long long ld_gxx, double *Gyx, l
     // latch the watchdog flag for the next synchronising call (stream-ordered; nothing waits here)
     NK_CUDA(h, cudaMemcpyAsync(h->gram_err_host, h->gram_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
     NK_CUDA(h, cudaGetLastError());
+    return NK_OK;
+}
+
+int nk_allreduce_grams(nk_handle *h, void *nccl_comm, double *packed, long long count, void *stream_) {
+    if (!h) return NK_E_INVALID;
+    if (!nccl_comm || !packed || count < 0) return set_err(h, NK_E_INVALID, "nk_allreduce_grams: bad argument");
+    if (count == 0) return NK_OK;
+    // int ncclAllReduce(const void *send, void *recv, size_t count, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);  nccl.h:
+    // ncclDouble = 8 (ncclFloat64), ncclSum = 0 -- stable across NCCL 2.x.  Resolved from the NCCL the HOST already loaded.
+    typedef int (*AllReduceFn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+    typedef const char *(*ErrStrFn)(int);
+    static AllReduceFn fn = nullptr;
+    static ErrStrFn errstr = nullptr;
+    if (!fn) {
+        fn = (AllReduceFn)dlsym(RTLD_DEFAULT, "ncclAllReduce");
+        errstr = (ErrStrFn)dlsym(RTLD_DEFAULT, "ncclGetErrorString");
+        if (!fn) {
+            for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+                void *lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD);      // already mapped by the host (e.g. torch's bundled copy)?
+                if (lib) { fn = (AllReduceFn)dlsym(lib, "ncclAllReduce"); errstr = (ErrStrFn)dlsym(lib, "ncclGetErrorString"); if (fn) break; }
+            }
+        }
+    }
+    if (!fn) return set_err(h, NK_E_STATE, "nk_allreduce_grams: no NCCL is loaded in this process (the host creates the communicator, so it must have loaded one)");
+    NK_ON_DEVICE(h);
+    const int rc = fn(packed, packed, (size_t)count, 8 /* ncclDouble */, 0 /* ncclSum */, nccl_comm, (cudaStream_t)stream_);
+    if (rc != 0) return set_err(h, NK_E_CUDA, std::string("ncclAllReduce: ") + (errstr ? errstr(rc) : "error ") + " (" + std::to_string(rc) + ")");
     return NK_OK;
 }
 

@@ -62,8 +62,11 @@ def test_estimator_matches_reference_golden(engine, path):
     if "K_lqr" in fx.files:
         Q = (1.0 if d != 192 else 0.005) * reg.C.T @ reg.C
         K, _ = O.dlqr(reg.A, reg.B, (Q + Q.T) / 2, np.eye(int(fx["n_inputs"])))     # DARE stays on the host (north star)
-        # Riccati gain: <=1e-9 where the reference itself reproduces it that well, else 10 x its own self-floor
-        assert O.relerr(K, fx["K_lqr"]) <= max(1e-9, 10.0 * float(fx["floor_K"])), (O.relerr(K, fx["K_lqr"]), float(fx["floor_K"]))
+        # Riccati gain: <=1e-9 where the reference itself reproduces it that well, else 10 x its own self-floor -- or, where one
+        # permutation happened to leave the gain almost unchanged (hjb_m30: floor_K 7e-10 next to floor_A 3e-7), as far as the
+        # model itself moves under that permutation
+        model_floor = float(fx["floor_A"]) + float(fx["floor_B"]) + float(fx["floor_C"])
+        assert O.relerr(K, fx["K_lqr"]) <= max(1e-9, 10.0 * float(fx["floor_K"]), model_floor), (O.relerr(K, fx["K_lqr"]), float(fx["floor_K"]))
 
 
 def test_landmark_draw_refit_and_pickle(engine):
