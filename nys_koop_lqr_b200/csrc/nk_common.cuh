@@ -96,13 +96,47 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // RBF (sklearn RBF.__call__): exp(-0.5 r^2);  Matern nu=2.5 (sklearn Matern.__call__): (1+a+a^2/3)exp(-a), a=sqrt(5) r.
 enum KernelKind : int { kRBF = 0, kMatern52 = 1 };
 
-// (A hand-rolled branch-free exp -- Cody-Waite reduction + degree-13 polynomial, 35% fewer FP64 instructions than the library
-// function -- was measured: no change in the fused kernel's throughput, so the 1-ulp library exp stays.)
+// exp(x) for x <= 0, BRANCH-FREE: Cody-Waite reduction (n = rint(x log2 e) through the 2^52+2^51 magic add, r = x - n ln2 in two
+// pieces), degree-13 Taylor polynomial in Horner form, scaling by 2^n as two exact power-of-two factors so that results in the
+// subnormal range (x < -708) are rounded once by the hardware and x <= -745.2 gives exactly 0 -- no special-case branch.
+// Within 1 ulp of the correctly rounded value (tests/test_gpu_kernels.py::test_kernel_function_accuracy gates 2 ulp against
+// numpy over the whole range).  What it buys is the control flow: the library exp carries a slow-path branch, which kept the compiler
+// from interleaving independent evaluations -- the lift epilogue of the fused kernel (64 per lane) ran them one after another,
+// a dependent chain of 16 FP64 operations each (measured 320 clk per value; profiles/r02_gram_timing.md).
+__device__ __forceinline__ double exp_nonpos(double x) {
+    x = fmax(x, -750.0);
+    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);
+    const int n = __double2loint(t);
+    const double nf = t - 6755399441055744.0;
+    double r = fma(nf, -6.93147180559945286227e-01, x);
+    r = fma(nf, -2.31904681384629955842e-17, r);
+    // Taylor polynomial of degree 13 on |r| <= ln2/2 (truncation 4e-18 relative), Horner form
+    double p = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600.0);
+    p = fma(r, p, 1.0 / 39916800.0);
+    p = fma(r, p, 1.0 / 3628800.0);
+    p = fma(r, p, 1.0 / 362880.0);
+    p = fma(r, p, 1.0 / 40320.0);
+    p = fma(r, p, 1.0 / 5040.0);
+    p = fma(r, p, 1.0 / 720.0);
+    p = fma(r, p, 1.0 / 120.0);
+    p = fma(r, p, 1.0 / 24.0);
+    p = fma(r, p, 1.0 / 6.0);
+    p = fma(r, p, 0.5);
+    p = fma(r, p, 1.0);
+    p = fma(r, p, 1.0);
+    const int n1 = n >> 1, n2 = n - n1;
+    const double s1 = __hiloint2double((n1 + 1023) << 20, 0), s2 = __hiloint2double((n2 + 1023) << 20, 0);
+    return (p * s1) * s2;
+}
+
+template <int KIND> __device__ __forceinline__ double kernel_from_exponent_t(double e) {
+    if (KIND == kRBF) return exp_nonpos(fmin(e, 0.0));
+    const double r2 = fmax(-2.0 * e, 0.0);
+    const double a = sqrt(r2) * 2.23606797749978969641;  // dists * sqrt(5)
+    return (1.0 + a + a * a / 3.0) * exp_nonpos(-a);
+}
 __device__ __forceinline__ double kernel_from_exponent(double e, int kind) {
-    if (kind == kRBF) return exp(fmin(e, 0.0));
-    double r2 = fmax(-2.0 * e, 0.0);
-    double a = sqrt(r2) * 2.23606797749978969641;  // dists * sqrt(5)
-    return (1.0 + a + a * a / 3.0) * exp(-a);
+    return kind == kRBF ? kernel_from_exponent_t<kRBF>(e) : kernel_from_exponent_t<kMatern52>(e);
 }
 
 }  // namespace nk

@@ -43,6 +43,7 @@ struct GramSmemCtl {
     uint64_t iq_empty[kItemQueue];
     QueuedItem iq[kItemQueue];
 };
+static_assert(sizeof(GramSmemCtl) <= kGramCtlBytes, "control block does not fit its reservation");
 
 // Dependence wait with a watchdog.  A wait that outlasts kSpinCap polls (each poll is an L2 round trip plus a 64 ns sleep, i.e.
 // roughly a microsecond: the cap is tens of seconds, a legitimate wait lasts microseconds), or that sees another CTA's timeout,
@@ -109,6 +110,41 @@ __device__ void do_pack(const GramParams &P, int chunk, int slot, int sb, int ti
             double *o = psi + packed_off(R, sb * kTile + s8 * 8, P.psi_rp);
 #pragma unroll
             for (int q = 0; q < 8; q += 2) st_v2_hint(o + q, v[q], v[q + 1], pol);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel-function epilogue of a lift item: the warp's 64x32 tile of exponents (staged in shared memory, fragment order) ->
+// kernel values -> packed feature chunk.  One fragment ROW block (8 landmarks x 32 samples: 4 column blocks, 8 values per lane)
+// per iteration, evaluated as straight-line branch-free code so that the eight independent polynomial chains interleave: the
+// first version went through the library exp one value at a time (a 16-deep dependent FP64 chain, 320 clk per value: the
+// epilogue cost 24 k clk per item against 53 k clk for the item's main loop).  Masking (padded landmarks, samples past n) is a
+// select after the evaluation.  Rolled over the 8 row blocks (fully unrolled it thrashed the instruction cache).
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ void lift_epilogue(const GramParams &P, uint32_t stg, int lane, int t, double *psi, long long s_chunk, int lm0,
+                                              int sl0, int R0, uint64_t pol, int i_begin, int i_end) {
+#pragma unroll 1
+    for (int i = i_begin; i < i_end; i++) {
+        double2 e[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) e[j] = lds_v2(stg + (uint32_t)((i - i_begin) * 4 + j) * 512u + lane * 16u);
+        double v[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            v[j][0] = kernel_from_exponent_t<KIND>(e[j].x);
+            v[j][1] = kernel_from_exponent_t<KIND>(e[j].y);
+        }
+        const bool lm_ok = (lm0 + i * 8) < P.m;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int s_local = sl0 + j * 8;
+            const long long s0 = s_chunk + s_local + 2 * t;
+            const double v0 = (lm_ok && s0 < P.n) ? v[j][0] : 0.0;
+            const double v1 = (lm_ok && (s0 + 1) < P.n) ? v[j][1] : 0.0;
+            double *o = psi + packed_off(R0 + i * 8, s_local, P.psi_rp) + lane * 2;
+            st_v2_hint(o, v0, v1, pol);
         }
     }
 }
@@ -232,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
         const uint32_t a_off = opaque(sm0 + (uint32_t)(wr * 8 * 2) * 512u + lane * 16u);            // A fragment (i=0,q=0) of stage 0
         const uint32_t b_off = opaque(sm0 + 16384u + (uint32_t)(wc * 4 * 2) * 512u + lane * 16u);  // B fragment (j=0,q=0) of stage 0
         const uint32_t full0 = opaque(smem_u32(&ctl->full[0])), empty0 = opaque(smem_u32(&ctl->empty[0]));
-        const uint32_t stg = opaque(sm0 + (uint32_t)kGramStageBytes + (uint32_t)warp * 16384u);  // this warp's 16 KB accumulator staging
+        const uint32_t stg = opaque(sm0 + (uint32_t)kGramStageBytes + (uint32_t)warp * (uint32_t)kStagingPerWarp);  // this warp's staging buffer
         // deferred completion signal of the previous syrk item of this warp (its bulk reduce is asynchronous)
         int *pend_ver = nullptr;
         int pend_par = 0;
@@ -357,52 +393,39 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                 const int slot = kMulti ? it.slot : (it.chunk & 1);
                 double *psi = P.PSI[slot];
                 const long long s_chunk = (long long)it.chunk * P.nk;
-#pragma unroll
-                for (int i = 0; i < 8; i++)
-#pragma unroll
-                    for (int j = 0; j < 4; j++) sts_v2(stg + (uint32_t)(i * 4 + j) * 512u + lane * 16u, acc[i][j][0], acc[i][j][1]);
-                __syncwarp();
-                const int kind = P.kind;
                 const int lm0 = it.b * kTile + wr * 64 + g;                       // landmark of fragment row block i = 0
                 const int sl0 = it.c * kTile + wc * 32;                           // first sample (chunk-local) of this warp tile
                 const int R0 = it.a * P.MP + it.b * kTile + wr * 64;              // first feature row of this warp tile
-#pragma unroll 1
-                for (int idx = 0; idx < 32; idx++) {
-                    const int i = idx >> 2, j = idx & 3;
-                    const double2 e = lds_v2(stg + (uint32_t)idx * 512u + lane * 16u);
-                    const int s_local = sl0 + j * 8;
-                    const long long s0 = s_chunk + s_local + 2 * t;
-                    const bool lm_ok = (lm0 + i * 8) < P.m;
-                    const double v0 = (lm_ok && s0 < P.n) ? kernel_from_exponent(e.x, kind) : 0.0;
-                    const double v1 = (lm_ok && (s0 + 1) < P.n) ? kernel_from_exponent(e.y, kind) : 0.0;
-                    double *o = psi + packed_off(R0 + i * 8, s_local, P.psi_rp) + lane * 2;
-                    st_v2_hint(o, v0, v1, pol_keep);
+                constexpr int kRowsPerPass = 8 / kStagingHalves;                  // fragment row blocks that fit the staging buffer
+#pragma unroll
+                for (int hh = 0; hh < kStagingHalves; hh++) {
+                    if (hh) __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < kRowsPerPass; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            sts_v2(stg + (uint32_t)(i * 4 + j) * 512u + lane * 16u, acc[hh * kRowsPerPass + i][j][0], acc[hh * kRowsPerPass + i][j][1]);
+                    __syncwarp();
+                    if (P.kind == kRBF) lift_epilogue<kRBF>(P, stg, lane, t, psi, s_chunk, lm0, sl0, R0, pol_keep, hh * kRowsPerPass, (hh + 1) * kRowsPerPass);
+                    else lift_epilogue<kMatern52>(P, stg, lane, t, psi, s_chunk, lm0, sl0, R0, pol_keep, hh * kRowsPerPass, (hh + 1) * kRowsPerPass);
                 }
+                TM_ADD(13, t_ep);          // (development build) the kernel-function loop alone
+                TM_START(t_fn);
                 fence_proxy_async();
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) atomicAdd(&P.counters[kCtrLift + slot], 1);
+                TM_ADD(14, t_fn);          // ... and the fences + signal that publish the tile
                 TM_ADD(7, t_ep);
             } else {
-                // Gram epilogue: accumulators -> this warp's 16 KB staging buffer -> one asynchronous bulk reduce-add
-                // (TMA engine, SASS UBLKRED.ADD.F64) into the fragment-ordered accumulator tile.  The warp does not wait
-                // for it: the completion signal is sent when the next item's main loop is over (flush_pending).  Chunk
-                // order per tile is enforced by the tile's version counter, so the summation order is fixed.
+                // Gram epilogue: accumulators -> this warp's staging buffer (8 KB: two passes of four fragment row blocks) ->
+                // asynchronous bulk reduce-adds (TMA engine, SASS UBLKRED.ADD.F64) into the fragment-ordered accumulator tile.
+                // The warp does not wait for the reduction: the completion signal is sent when the next item's main loop is
+                // over (flush_pending).  Chunk order per tile is enforced by the tile's version counter, so the summation
+                // order is fixed.
                 int *ver = &P.counters[kCounterTileVer + it.c];
-#pragma unroll
-                for (int i = 0; i < 8; i++)
-#pragma unroll
-                    for (int j = 0; j < 4; j++) sts_v2(stg + (uint32_t)(i * 4 + j) * 512u + lane * 16u, acc[i][j][0], acc[i][j][1]);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) {
-                    if (spin_until_ge(ver, it.chunk * kConsumerWarps, P.err)) {
-                        double *gt = P.Gws + (size_t)it.c * (kTile * kTile) + (size_t)warp * 32 * kBlk;
-                        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
-                                     ::"l"(gt), "r"(stg), "r"(16384) : "memory");
-                    }
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
+                constexpr int kRowsPerPass = 8 / kStagingHalves;
+                bool tile_ok = true;
                 pend_ver = ver;
                 pend_par = kMulti ? it.slot : (it.chunk & 1);
                 if (kMulti) flush_pending();   // small problems: the same tile of the next chunk (another CTA) is waiting for this

@@ -46,11 +46,24 @@ struct GramParams {
 constexpr int kCtrPack = 16, kCtrLift = 32, kCtrSyrk = 48;
 constexpr int kCounterTileVer = 64;
 constexpr unsigned kSpinCap = 1u << 25;   // polls of a dependence wait before the watchdog fires (~1 us each)
-constexpr int kGramStages = 3;
+// Operand ring depth: 5 stages of 2 x 16 KB slabs (160 KB) + 8 KB of accumulator / exponent staging per consumer warp (epilogues
+// run in two passes of four fragment row blocks).  The first version had 3 stages + 16 KB staging (-DNK_GRAM_STAGES=3 still builds
+// it); the deeper ring measured +0.4% at m = 4096.  Measured dead ends of round 2 (profiles/r02_gram_kernel_experiments.md):
+// running the two warps of an SM sub-partition 1..4 slabs out of phase so that one's epilogue overlaps the other's main loop
+// (-1.2 ... -2.2%: one warp alone cannot keep the FP64 tensor pipe fed, the lock-step pair can), and handing the reduce-add +
+// completion signal of a finished Gram item to helper lanes of the producer warpgroup (-1.3%: the consumers' epilogue shrank
+// by 1.6 k clk per item but their main loop grew by 2.7 k).
+#ifndef NK_GRAM_STAGES
+#define NK_GRAM_STAGES 5
+#endif
+constexpr int kGramStages = NK_GRAM_STAGES;
+constexpr int kStagingPerWarp = kGramStages > 3 ? 8192 : 16384;
+constexpr int kStagingHalves = 16384 / kStagingPerWarp;
 constexpr int kItemQueue = 4;
 constexpr size_t kGramStageBytes = (size_t)kGramStages * 2 * kSlabTileDoubles * 8;      // 96 KB operand ring
-constexpr size_t kGramStagingBytes = (size_t)kConsumerWarps * 16384;                    // 128 KB accumulator staging
-constexpr size_t kGramSmemBytes = kGramStageBytes + kGramStagingBytes + 512;
+constexpr size_t kGramStagingBytes = (size_t)kConsumerWarps * kStagingPerWarp;           // accumulator / exponent staging
+constexpr size_t kGramCtlBytes = 1024;
+constexpr size_t kGramSmemBytes = kGramStageBytes + kGramStagingBytes + kGramCtlBytes;
 
 void launch_gram(const GramParams &P, int sm_count, cudaStream_t stream, cudaError_t *err);
 

@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of development builds of the fused kernel: tools/ab_probe.sh <n> <m> lib1 lib2 ...
+# A/B of development builds of the fused kernel: tools/ab_probe.sh <n> <m> lib1 lib2 ...   (libs live in build_variants/)
 n=$1; m=$2; shift 2
 for lib in "$@"; do
   echo "== $lib"

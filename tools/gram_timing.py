@@ -10,7 +10,7 @@ sys.path.insert(0, ".")
 from nys_koop_lqr_b200.engine import Engine
 
 NAMES = ["total", "wait_item", "pack", "wait_first_slab", "mainloop_lift", "mainloop_syrk", "flush_pending", "epilogue_lift",
-         "epilogue_syrk", "n_lift", "n_syrk", "midloop_wait_cycles", "midloop_waits"]
+         "epilogue_syrk", "n_lift", "n_syrk", "midloop_wait_cycles", "midloop_waits", "lift_kernel_function_loop", "lift_publish_fences"]
 
 
 def main(n=200000, m=4096, d=192, p=6, chunk=512):
@@ -40,6 +40,13 @@ def main(n=200000, m=4096, d=192, p=6, chunk=512):
     # ideal main-loop cycles: DMMAs per warp x 16 clk x 2 warps per sub-partition
     KLS = (d + 2 + 15) // 16
     ideal = (t[:, :, 9] * KLS + t[:, :, 10] * (chunk // 16)) * 128 * 32
+    out["cycles_per_lift_epilogue"] = float((t[:, :, 7].sum() / max(t[:, :, 9].sum(), 1)))
+    out["cycles_per_lift_function_loop"] = float((t[:, :, 13].sum() / max(t[:, :, 9].sum(), 1)))
+    out["cycles_per_lift_publish"] = float((t[:, :, 14].sum() / max(t[:, :, 9].sum(), 1)))
+    out["cycles_per_syrk_epilogue"] = float((t[:, :, 8].sum() / max(t[:, :, 10].sum(), 1)))
+    out["cycles_per_syrk_flush"] = float((t[:, :, 6].sum() / max((t[:, :, 9] + t[:, :, 10]).sum(), 1)))
+    out["cycles_per_syrk_mainloop"] = float((t[:, :, 5].sum() / max(t[:, :, 10].sum(), 1)))
+    out["cycles_per_lift_mainloop"] = float((t[:, :, 4].sum() / max(t[:, :, 9].sum(), 1)))
     out["mainloop_ideal_frac_of_total"] = float((ideal / t[:, :, 0]).mean())
     out["mainloop_measured_frac_of_total"] = out["mainloop_lift"] + out["mainloop_syrk"]
     print(json.dumps(out, indent=1))
