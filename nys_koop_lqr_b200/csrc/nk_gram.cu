@@ -24,11 +24,11 @@
 // global memory, so there is no grid-wide barrier and the summation order is fixed (deterministic results).
 //
 // CTA = 8 consumer warps (2 x 4, warp tile 64 x 32, 64 FP64 accumulators per lane) + 1 producer warp that
-// claims items one ahead, resolves their dependences and feeds a 3-stage ring of 2 x 16 KB operand slabs with
-// cp.async.bulk (TMA engine, mbarrier transaction counts); 128 KB of shared memory stage the accumulator tiles
-// for the asynchronous bulk reduce-add of the Gram epilogue and the exponents of the kernel-function epilogue.
-// Measured dead ends: two 4-warp CTAs per SM as a ping-pong (-1.5%: the 168-register budget
-// costs the cross-step fragment prefetch), spreading the fragment loads, more ILP in the kernel-function loop.
+// claims items one ahead, resolves their dependences and feeds a 5-stage ring of 2 x 16 KB operand slabs with
+// cp.async.bulk (TMA engine, mbarrier transaction counts); 8 KB of shared memory per consumer warp stage the
+// accumulator tiles for the asynchronous bulk reduce-adds of the Gram epilogue and the exponents of the kernel-function
+// epilogue (two passes each).  Measured dead ends (profiles/r02_gram_kernel_experiments.md): two 4-warp
+// CTAs per SM as a ping-pong, the two halves of one CTA out of phase, helper lanes for the completion signal.
 #include "nk_gram.cuh"
 #include "nk_mainloop.cuh"
 
@@ -426,6 +426,29 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams P) {
                 int *ver = &P.counters[kCounterTileVer + it.c];
                 constexpr int kRowsPerPass = 8 / kStagingHalves;
                 bool tile_ok = true;
+#pragma unroll
+                for (int hh = 0; hh < kStagingHalves; hh++) {
+                    if (hh) {      // the engine must have READ the previous pass out of the staging buffer before it is overwritten
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int i = 0; i < kRowsPerPass; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            sts_v2(stg + (uint32_t)(i * 4 + j) * 512u + lane * 16u, acc[hh * kRowsPerPass + i][j][0], acc[hh * kRowsPerPass + i][j][1]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (hh == 0) tile_ok = spin_until_ge(ver, it.chunk * kConsumerWarps, P.err);
+                        if (tile_ok) {
+                            double *gt = P.Gws + (size_t)it.c * (kTile * kTile) + (size_t)warp * 32 * kBlk + (size_t)hh * (kStagingPerWarp / 8);
+                            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
+                                         ::"l"(gt), "r"(stg), "r"(kStagingPerWarp) : "memory");
+                        }
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
                 pend_ver = ver;
                 pend_par = kMulti ? it.slot : (it.chunk & 1);
                 if (kMulti) flush_pending();   // small problems: the same tile of the next chunk (another CTA) is waiting for this

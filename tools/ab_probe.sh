@@ -3,10 +3,12 @@
 n=$1; m=$2; shift 2
 for lib in "$@"; do
   echo "== $lib"
-  NK_LIB_PATH=$PWD/build_variants/$lib timeout -s KILL 300 python tools/perf_probe.py $n $m 192 6 512 2 2>&1 | tail -2 | python -c "
+  NK_LIB_PATH=$PWD/build_variants/$lib timeout -s KILL 300 python tools/perf_probe.py $n $m 192 6 512 2 2>&1 | tail -3 | python -c "
 import sys, json
 for l in sys.stdin:
-    try: d = json.loads(l); print('   %.1f ms  %.0f samples/s  frac %.4f' % (d['ms'], d['samples_per_s'], d['frac_of_37_1']))
+    try:
+        d = json.loads(l)
+        print(('   check ok=%s max_rel_err=%.1e' % (d['ok'], d['max_rel_err'])) if 'check' in d else ('   %.1f ms  %.0f samples/s  frac %.4f' % (d['ms'], d['samples_per_s'], d['frac_of_37_1'])))
     except Exception: print(l.strip())
 "
 done

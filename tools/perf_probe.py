@@ -24,6 +24,19 @@ def main(n=400000, m=4096, d=192, p=6, chunk=512, reps=2):
         F = 4.0 * m * m + 6.0 * m * d + 4.0 * m * p
         print(json.dumps(dict(n=n, m=m, d=d, chunk=chunk, ms=ms, samples_per_s=n / ms * 1e3, algo_tflops=F * n / ms * 1e-9,
                               exec_tflops=eng.gram_executed_flops() / ms * 1e-9, frac_of_37_1=F * n / ms * 1e-9 / 37.1)))
+    # a perf number of a kernel that computes the wrong thing is worthless: check a small pass against an independent device path
+    ns = 2048
+    Gs = eng.grams(Xa[:ns], Y[:ns], Z, il, 0, p, chunk)
+    Kx = eng.kernel_cross(Z, Xa[:ns, :d].contiguous(), il, 0)
+    Ky = eng.kernel_cross(Z, Y[:ns].contiguous(), il, 0)
+    U = Xa[:ns, d:]
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    errs = dict(Gxx=rel(Gs["Gxx"], Kx @ Kx.T), Gyx=rel(Gs["Gyx"], Ky @ Kx.T), Gyy=rel(Gs["Gyy"], Ky @ Ky.T), Gxu=rel(Gs["Gxu"], Kx @ U),
+                Guu=rel(Gs["Guu"], U.T @ U), GYy=rel(Gs["GYy"], Y[:ns].T @ Ky.T))
+    ok = max(errs.values()) <= 1e-11
+    print(json.dumps(dict(check="fused Grams of the first %d samples vs kernel_cross + torch matmul" % ns, ok=ok, max_rel_err=max(errs.values()))))
+    if not ok:
+        raise SystemExit("perf_probe: WRONG RESULTS " + json.dumps(errs))
     return G
 
 if __name__ == "__main__":
