@@ -248,6 +248,11 @@ def parity_check(args, eng, R, kernel, world, rank, dist, torch):
     path is fit_distributed on the sharded prefix (allreduce and sharded solve included); rank 0 runs the oracle."""
     from nys_koop_lqr_b200 import sharding
     from oracle import nk_oracle as O
+    try:        # all host threads for the oracle's BLAS, also when torchrun exported OMP_NUM_THREADS=1 before numpy was loaded
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:  # noqa: BLE001
+        pass
     m, d, p = args.m, args.d, args.p
     n = max(int(args.parity_samples), m)
     Xs, U, Y = O.synthetic(n, d, p, seed=2024)
@@ -340,7 +345,12 @@ def run_gpu_arm(args):
         if distributed:
             reg.fit_distributed(Xin, Yin)
             if rank == 0:                                          # results are read on the host once per node: rank 0
+                t0_ = time.perf_counter()
                 _ = (reg.A, reg.B, reg.C, reg.weights)             # downloads them INSIDE the timed region; the other ranks keep theirs on the device
+                if getattr(reg, "profile_", None) is not None:
+                    reg.profile_["download_ms"] = (time.perf_counter() - t0_) * 1e3
+            if getattr(reg, "profile_", None):
+                print(f"[bench rank {rank}] fit_distributed phases (ms): " + json.dumps({k: round(v, 1) for k, v in reg.profile_.items()}), file=sys.stderr)
         else:
             reg.fit(Xin, Yin)
         return reg

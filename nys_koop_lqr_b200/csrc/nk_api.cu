@@ -166,6 +166,9 @@ int nk_destroy(nk_handle *h) {
     for (int s = 0; s < kMaxSlots; s++) for (nk_devbuf *b : {&h->xp[s], &h->yp[s], &h->psi[s]}) if (b->ptr) cudaFree(b->ptr);
     for (nk_devbuf &b : h->dense) if (b.ptr) cudaFree(b.ptr);
     if (h->gram_err_host) cudaFreeHost(h->gram_err_host);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
     return NK_OK;
 }

@@ -841,6 +841,44 @@ int nk_solve_abc_part(nk_handle *h, int m, int p, int d, double gamma_n, double 
     const long long ldkin = same_landmarks ? L->ld_kzz : L->ld_kzz_in;
     NK_CUDA(h, cudaMemsetAsync(dinfo, 0, 2 * sizeof(int), stream));
 
+    // ---- reconstruction: C = GYy (gn Kmm + Gyy)^-1 S   (regressors.py:162-166), rows of C^T = columns of C ----
+    // Independent of the dynamics solve, and both are latency-bound (a chain of 128x128 diagonal-block kernels): when both are
+    // asked for, this one is queued FIRST, on the handle's side stream with its own scratch (forked from the caller's stream here,
+    // joined after the dynamics block), so that the two chains interleave on the device.
+    if (c_rows > 0) {
+        const bool concurrent = g_rows > 0;
+        cudaStream_t st2 = stream;
+        double *rec, *Lt2, *Pt, *dinv2, *dinvT2;
+        if (concurrent) {
+            if (!h->side_stream) {
+                NK_CUDA(h, cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+                NK_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+                NK_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+            }
+            st2 = h->side_stream;
+            rec = dense_scratch(h, 16, (size_t)m * ldm, &rc); if (rc) return rc;
+            Lt2 = dense_scratch(h, 17, (size_t)m * ldm, &rc); if (rc) return rc;
+            Pt = dense_scratch(h, 18, (size_t)c_rows * ldm + 2, &rc); if (rc) return rc;
+            dinv2 = dense_scratch(h, 19, (size_t)nblk1 * kDB * kDB, &rc); if (rc) return rc;
+            dinvT2 = dense_scratch(h, 20, (size_t)nblk1 * kDB * kDB, &rc); if (rc) return rc;
+        } else {
+            rec = inner; Lt2 = Lt; Pt = Rt; dinv2 = dinv; dinvT2 = dinvT;
+        }
+        if (concurrent) {      // fork: everything already queued on the caller's stream (the Grams!) precedes the side stream's work
+            NK_CUDA(h, cudaEventRecord(h->ev_fork, stream));
+            NK_CUDA(h, cudaStreamWaitEvent(st2, h->ev_fork, 0));
+        }
+        launch2d(m, m, grid, block);
+        assemble_rec_kernel<<<grid, block, 0, st2>>>(m, gamma_n, jitter, G->Gyy, G->ld_gyy, L->Kzz, L->ld_kzz, rec, ldm);
+        h->launches++;
+        potrf_blocked(h, m, rec, ldm, Lt2, ldm, dinv2, dinvT2, dinfo + 1, st2);
+        NK_CUDA(h, cudaMemcpy2DAsync(Pt, (size_t)ldm * 8, L->S + (long long)c_row0 * L->ld_s, (size_t)L->ld_s * 8, (size_t)m * 8, c_rows,
+                                     cudaMemcpyDeviceToDevice, st2));                            // rows of S^T = S
+        trsm_fwd_t(h, m, c_rows, rec, ldm, dinv2, Pt, ldm, st2);
+        trsm_bwd_t(h, m, c_rows, Lt2, ldm, dinvT2, Pt, ldm, st2);                                // rows of (inner_rec^-1 S)^T
+        gemm_nt(h, c_rows, d, m, 1.0, Pt, ldm, G->GYy, G->ld_gYy, 0.0, CT, ld_ct, 0.0, 0, nullptr, 0, st2);   // C^T rows
+        if (concurrent) NK_CUDA(h, cudaEventRecord(h->ev_join, st2));
+    }
     // ---- dynamics: G = S^-1 [Gyx|Gyu] inner^-1 blkdiag(K_io S^-1, I)   (regressors.py:147-159), rows of G^T = columns of G ----
     if (g_rows > 0) {
         launch2d(N1, N1, grid, block);
@@ -872,20 +910,8 @@ int nk_solve_abc_part(nk_handle *h, int m, int p, int d, double gamma_n, double 
         // G^T rows = sol^T rows * left^T      [G = left sol]
         gemm_nt(h, g_rows, m, N1, 1.0, Rt, ld1, left, ld1, 0.0, GT, ld_gt, 0.0, 0, nullptr, 0, stream);
     }
+    if (g_rows > 0 && c_rows > 0) NK_CUDA(h, cudaStreamWaitEvent(stream, h->ev_join, 0));     // join the reconstruction solve
 
-    // ---- reconstruction: C = GYy (gn Kmm + Gyy)^-1 S   (regressors.py:162-166), rows of C^T = columns of C ----
-    if (c_rows > 0) {
-        double *rec = inner, *Lt2 = Lt, *Pt = Rt;
-        launch2d(m, m, grid, block);
-        assemble_rec_kernel<<<grid, block, 0, stream>>>(m, gamma_n, jitter, G->Gyy, G->ld_gyy, L->Kzz, L->ld_kzz, rec, ldm);
-        h->launches++;
-        potrf_blocked(h, m, rec, ldm, Lt2, ldm, dinv, dinvT, dinfo + 1, stream);
-        NK_CUDA(h, cudaMemcpy2DAsync(Pt, (size_t)ldm * 8, L->S + (long long)c_row0 * L->ld_s, (size_t)L->ld_s * 8, (size_t)m * 8, c_rows,
-                                     cudaMemcpyDeviceToDevice, stream));                         // rows of S^T = S
-        trsm_fwd_t(h, m, c_rows, rec, ldm, dinv, Pt, ldm, stream);
-        trsm_bwd_t(h, m, c_rows, Lt2, ldm, dinvT, Pt, ldm, stream);                              // rows of (inner_rec^-1 S)^T
-        gemm_nt(h, c_rows, d, m, 1.0, Pt, ldm, G->GYy, G->ld_gYy, 0.0, CT, ld_ct, 0.0, 0, nullptr, 0, stream);   // C^T rows
-    }
     int hinfo[2] = {0, 0};
     NK_CUDA(h, cudaMemcpyAsync(hinfo, dinfo, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
     NK_CUDA(h, cudaStreamSynchronize(stream));      // the one synchronisation of this call: the two Cholesky verdicts

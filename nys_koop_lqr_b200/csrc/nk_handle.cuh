@@ -31,8 +31,12 @@ struct nk_handle {
     std::vector<int> h_tile_of;
 
     // ---- dense-stage scratch (grow-only), see nk_dense.cu ----
-    nk_devbuf dense[16];
+    nk_devbuf dense[24];
     nk_devbuf dinfo;
+    // side stream + events of nk_solve_abc_part: the two regularised systems are independent and each is latency-bound
+    // (serial 128x128 diagonal blocks), so the reconstruction solve runs beside the dynamics solve
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace nk {

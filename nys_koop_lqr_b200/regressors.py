@@ -185,6 +185,7 @@ class KoopmanNystromRegressor(KoopmanRegressor):
     stream_block = 262144     # samples per host->device block when inputs live in host memory
     device_block = 1 << 24    # samples per fused-kernel launch when inputs are already on the device
     gram_chunk = 0            # samples per on-chip feature chunk (0: library default 512)
+    pinned_results = True     # A / B / C / weights are numpy views of one page-locked buffer per fit (False: pageable copies)
 
     def __init__(self, n_inputs, kernel=None, gamma=None, m=None):
         super().__init__(n_inputs, gamma, m)
@@ -373,7 +374,10 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         names = [k for k in ("A", "B", "C", "weights") if k in pend]
         tensors = [pend[k] for k in names]
         total = sum(t.numel() for t in tensors)
-        host = eng.pinned_staging(total)
+        # One page-locked buffer per fit, taken from torch's caching host allocator (a cache hit after the first fit of a
+        # process); the numpy attributes are VIEWS of it -- no second, first-touch copy on the host (that copy was 10 of the 12 ms
+        # of a 147 MB result download).  The buffer lives as long as any of the arrays does.
+        host = torch.empty(int(total), dtype=torch.float64, pin_memory=True) if self.pinned_results else eng.pinned_staging(total)
         main = torch.cuda.current_stream(eng.tdev)
         o, slots = 0, []
         for t in tensors:
@@ -383,7 +387,8 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         main.synchronize()
         arr = host.numpy()
         for k, (off, shape) in zip(names, slots):
-            self.__dict__["_" + k] = _host_copy(arr[off:off + int(np.prod(shape))].reshape(shape))
+            view = arr[off:off + int(np.prod(shape))].reshape(shape)
+            self.__dict__["_" + k] = view if self.pinned_results else _host_copy(view)
         self._d2h_bytes = int(total) * 8
         self.__dict__["_pending"] = {}
 
@@ -460,6 +465,7 @@ class KoopmanNystromRegressor(KoopmanRegressor):
             columns of [A|B] and m/G columns of C (``nk_solve_abc_part``), and two all-gathers assemble G^T and C^T;
           * the results stay on the device until somebody reads them: ``materialize="lazy"`` (default) downloads A / B / C /
             weights on first attribute access on the ranks that look, ``"all"`` downloads on every rank before returning."""
+        import time
         import torch
         import torch.distributed as dist
         from . import sharding
@@ -468,16 +474,30 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         d = int(X_local.shape[1]) - self.n_inputs
         p = self.n_inputs
         world, rank = dist.get_world_size(group), dist.get_rank(group)
+        prof = {} if os.environ.get("NK_PROFILE") else None      # per-phase wall times (device-synchronised) in self.profile_
+
+        def tick(name, t0):
+            if prof is None:
+                return 0.0
+            torch.cuda.synchronize(eng.tdev)
+            now = time.perf_counter()
+            if name:
+                prof[name] = prof.get(name, 0.0) + (now - t0) * 1e3
+            return now
+        t = tick(None, 0.0)
         n_total, off = sharding.global_layout(n_local, group, eng.tdev)
         if self.nystrom_centers_output is None:
             self._draw_shared_landmarks(n_total, off, n_local, Y_local, d, group, eng.tdev)
         self._ensure_centers(None, n_total)
         split = head_rank is not None and world > 1
+        t = tick("layout_ms", t)
 
         def local_stage():
+            nonlocal t
             dev = self._device_state(d, landmark_stage=not split)
             self._accumulate_grams(eng, dev, X_local, Y_local)
             G = eng.gram_finalize()
+            t = tick("gram_pass_ms", t)
             lm = None
             if split and dev.get("S") is None:
                 m = dev["Z"].shape[0]
@@ -487,14 +507,18 @@ class KoopmanNystromRegressor(KoopmanRegressor):
                     self._landmark_stage(dev)
                     for i, k in enumerate(("Kzz", "S", "Sinv", "Kzz_in", "Kio")[:nmat]):
                         lm[i].copy_(dev[k])
+                t = tick("landmark_stage_ms", t)
             return dev, G, lm
         dev, G, lm = self._agree(group, eng.tdev, local_stage, "fit_distributed: Gram pass / landmark stage")
+        t = tick("wait_for_slowest_rank_ms", t)
         sharding.allreduce_grams(G["_flat"], group)                                   # the only data-path collective
+        t = tick("allreduce_ms", t)
         if lm is not None:
             dist.broadcast(lm, src=dist.get_global_rank(group, head_rank) if group is not None else head_rank, group=group)
             dev.update(Kzz=lm[0], S=lm[1], Sinv=lm[2])
             if lm.shape[0] == 5:
                 dev.update(Kzz_in=lm[3], Kio=lm[4])
+            t = tick("broadcast_ms", t)
         # ---- column-sharded solve ----
         m = dev["Z"].shape[0]
         N1 = m + p
@@ -508,10 +532,14 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         part = lambda: eng.solve_abc_part(G, dev["Kzz"], dev["S"], dev["Sinv"], gamma_n, g_rows, c_rows, GT_mine, CT_mine, self.jitter,
                                           Kzz_in=dev["Kzz_in"], Kio=dev["Kio"])
         self._agree(group, eng.tdev, lambda: self._solve_guarded(part, G), "fit_distributed: regularised solves")
+        t = tick("sharded_solve_ms", t)
         sharding.gather_rows(GT_all, GT_mine, group)
         sharding.gather_rows(CT_all, CT_mine, group)
         A, B, C, W = eng.solve_abc_finish(GT_all, CT_all, m, p, d)
+        t = tick("gather_finish_ms", t)
         self._set_device_results(dev, A, B, C, W, eager=(materialize == "all"))
+        t = tick("materialize_ms", t)
+        self.profile_ = prof
 
     def fit_cv(self, X, Y, kernels, gammas, n_splits=5, refit=True):
         """Batched hyper-parameter search: the reference's ``learn_hyperparams`` (benchmark_lqr_cloth.py:39-66,
