@@ -374,10 +374,14 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         names = [k for k in ("A", "B", "C", "weights") if k in pend]
         tensors = [pend[k] for k in names]
         total = sum(t.numel() for t in tensors)
-        # One page-locked buffer per fit, taken from torch's caching host allocator (a cache hit after the first fit of a
-        # process); the numpy attributes are VIEWS of it -- no second, first-touch copy on the host (that copy was 10 of the 12 ms
-        # of a 147 MB result download).  The buffer lives as long as any of the arrays does.
-        host = torch.empty(int(total), dtype=torch.float64, pin_memory=True) if self.pinned_results else eng.pinned_staging(total)
+        # One page-locked buffer per fit from the engine's pool (reused once the arrays of an earlier fit are gone); the numpy
+        # attributes are VIEWS of it -- no second, first-touch copy on the host (that copy was 10 of the 12 ms of a 147 MB
+        # result download).  The buffer stays out of the pool as long as any of the arrays lives.
+        if self.pinned_results:
+            host, arr = eng.result_buffer(total)
+        else:
+            host = eng.pinned_staging(total)
+            arr = host.numpy()
         main = torch.cuda.current_stream(eng.tdev)
         o, slots = 0, []
         for t in tensors:
@@ -385,7 +389,6 @@ class KoopmanNystromRegressor(KoopmanRegressor):
             host[o:o + t.numel()].copy_(t.reshape(-1), non_blocking=True)
             o += t.numel()
         main.synchronize()
-        arr = host.numpy()
         for k, (off, shape) in zip(names, slots):
             view = arr[off:off + int(np.prod(shape))].reshape(shape)
             self.__dict__["_" + k] = view if self.pinned_results else _host_copy(view)

@@ -173,3 +173,25 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
         assert r.returncode == 0 and r.stdout.startswith("ok ")
     else:
         assert r.returncode == 3 and r.stdout.startswith("-2 ") and "no CPU fallback" in r.stdout
+
+
+def test_result_buffer_pool_never_hands_out_a_viewed_buffer():
+    """Result arrays are numpy VIEWS of a pooled page-locked buffer: the pool may reuse it only when every view is gone."""
+    import gc
+    import torch
+    from nys_koop_lqr_b200.engine import Engine
+    eng = Engine.__new__(Engine)                      # the pool logic needs no device; allocate pageable memory here
+    alloc = lambda n: torch.empty(n, dtype=torch.float64)
+    a, arr = eng.result_buffer(100, alloc)
+    view = arr[10:30].reshape(4, 5)
+    ptr = a.data_ptr()
+    del a, arr
+    b, arr_b = eng.result_buffer(50, alloc)
+    assert b.data_ptr() != ptr and len(eng._result_pool) == 2      # `view` still looks at the first buffer
+    view[:] = 7.0
+    del view
+    gc.collect()
+    c, arr_c = eng.result_buffer(80, alloc)
+    assert c.data_ptr() == ptr and len(eng._result_pool) == 2      # ... now it is free again
+    d, _ = eng.result_buffer(1000, alloc)                           # too small buffers are not reused
+    assert d.numel() >= 1000 and len(eng._result_pool) == 3
