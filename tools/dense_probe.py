@@ -70,4 +70,4 @@ def main(ms=(4096, 8192), nb=100000, steps=4):
 
 
 if __name__ == "__main__":
-    main()
+    main(ms=tuple(int(a) for a in sys.argv[1:]) or (4096, 8192))
