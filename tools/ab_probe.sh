@@ -3,7 +3,7 @@
 n=$1; m=$2; shift 2
 for lib in "$@"; do
   echo "== $lib"
-  NK_LIB_PATH=$PWD/build_variants/$lib timeout -s KILL 300 python tools/perf_probe.py $n $m 192 6 512 2 2>&1 | tail -3 | python -c "
+  NK_LIB_PATH=$PWD/build_variants/$lib timeout -s KILL 300 python tools/perf_probe.py $n $m 192 6 ${CHUNK:-512} 2 2>&1 | tail -3 | python -c "
 import sys, json
 for l in sys.stdin:
     try:
