@@ -281,6 +281,38 @@ __global__ void rowsum_max_kernel(int n, const double *A, long long lda, double 
 }
 static void launch2d(int rows, int cols, dim3 &grid, dim3 &block) { block = dim3(128); grid = dim3((cols + 127) / 128, rows); }
 
+// ---- helpers of the symmetric square root's spectrum estimate and convergence check ----
+// rows of +-1 from a fixed hash: the start vectors of the inverse iteration (deterministic)
+__global__ void probe_init_kernel(int rows, int n, double *V, long long ld) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c >= n) return;
+    unsigned x = (unsigned)(c * 8 + r) * 2654435761u;
+    x ^= x >> 15; x *= 2246822519u; x ^= x >> 13;
+    V[(long long)r * ld + c] = (x & 1u) ? 1.0 : -1.0;
+}
+// out[r] = || V[r, :] ||_2, one CTA per row, fixed-order tree (deterministic)
+__global__ void row_norm_kernel(int n, const double *V, long long ld, double *out) {
+    const int r = blockIdx.x;
+    double s = 0.0;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) { const double v = V[(long long)r * ld + c]; s += v * v; }
+    __shared__ double red[256];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) out[r] = sqrt(red[0]);
+}
+// out[0] = max_{r,c} | T(r,c) - [r == c] |   (out zeroed by the caller; non-negative doubles order like their bit patterns)
+__global__ void max_dev_identity_kernel(int n, const double *T, long long ld, double *out) {
+    const int r = blockIdx.x;
+    double s = 0.0;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) s = fmax(s, fabs(T[(long long)r * ld + c] - (r == c ? 1.0 : 0.0)));
+    __shared__ double red[256];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]); __syncthreads(); }
+    if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long *>(out), (unsigned long long)__double_as_longlong(red[0]));
+}
+
 // centre = column means of the landmarks (any shift is valid: distances are shift invariant; the mean minimises the norms
 // entering the expansion).  32 columns x 32 row lanes per CTA, fixed-order tree over the row lanes -> deterministic.
 __global__ void landmark_center_kernel2(const double *Z, long long ldz, int m, int d, double *center) {
@@ -716,7 +748,7 @@ int nk_sym_sqrt(nk_handle *h, int n, const double *K, long long ldk, double lamb
     double *T = dense_scratch(h, 6, nn, &rc); if (rc) return rc;
     double *dinv = dense_scratch(h, 8, (size_t)nblk * kDB * kDB, &rc); if (rc) return rc;
     double *dinvT = dense_scratch(h, 9, (size_t)nblk * kDB * kDB, &rc); if (rc) return rc;
-    if ((rc = ensure(h, h->dinfo, 64)) != NK_OK) return rc;
+    if ((rc = ensure(h, h->dinfo, 256)) != NK_OK) return rc;
     int *dinfo = (int *)h->dinfo.ptr;
     double *dnorm = (double *)((char *)h->dinfo.ptr + 16);
 
@@ -724,11 +756,39 @@ int nk_sym_sqrt(nk_handle *h, int n, const double *K, long long ldk, double lamb
     NK_CUDA(h, cudaMemsetAsync(dnorm, 0, 8, stream));
     rowsum_max_kernel<<<n, 256, 0, stream>>>(n, L, ldn, dnorm);
     potrf_blocked(h, n, L, ldn, Lt, ldn, dinv, dinvT, dinfo, stream);
-    struct { int info; int pad[3]; double nrm2; } host;
-    NK_CUDA(h, cudaMemcpyAsync(&host, h->dinfo.ptr, 24, cudaMemcpyDeviceToHost, stream));
+    // Spectrum estimate (large matrices only: it costs ~12 sweeps of small launches).  The Newton-Schulz schedule below starts from
+    // a lower bound l on sigma_min(L^T) / ||L^T||; the only GUARANTEED one is sqrt(lambda_min_bound) -- the jitter, 1e-6 -- which at
+    // m = 4096 on the benchmark's kernel matrix (cond 2e3) is 1000 x too pessimistic and costs 6-7 of 17 iterations.  A few steps of
+    // inverse iteration with the factor just computed (8 fixed +-1 start vectors, v <- K^-1 v through the transposed-storage
+    // triangular sweeps) give lambda_est = min_r |v_5| / |v_6| >= lambda_min, within a few percent after 6 steps; the schedule uses a
+    // quarter of it, and the residual check after the scheduled iterations catches an estimate that was still too optimistic.
+    constexpr int kProbeRows = 8, kProbeSteps = 6;
+    const bool estimate = n >= 1024;
+    double *dprobe = dnorm + 1;     // [1..8]: |v_5|, [9..16]: |v_6|, [17]: residual of the convergence check
+    if (estimate) {
+        double *V = X;              // (8, n) in the scratch the iteration will overwrite afterwards
+        dim3 g2((n + 127) / 128, kProbeRows);
+        probe_init_kernel<<<g2, 128, 0, stream>>>(kProbeRows, n, V, ldn);
+        for (int st = 0; st < kProbeSteps; st++) {
+            if (st == kProbeSteps - 1) row_norm_kernel<<<kProbeRows, 256, 0, stream>>>(n, V, ldn, dprobe);
+            trsm_fwd_t(h, n, kProbeRows, L, ldn, dinv, V, ldn, stream);
+            trsm_bwd_t(h, n, kProbeRows, Lt, ldn, dinvT, V, ldn, stream);
+        }
+        row_norm_kernel<<<kProbeRows, 256, 0, stream>>>(n, V, ldn, dprobe + kProbeRows);
+        h->launches += 3;
+    }
+    struct { int info; int pad[3]; double nrm2; double probe[2 * kProbeRows]; } host;
+    NK_CUDA(h, cudaMemcpyAsync(&host, h->dinfo.ptr, sizeof(host), cudaMemcpyDeviceToHost, stream));
     NK_CUDA(h, cudaStreamSynchronize(stream));
     if (host.info != 0) return set_err(h, NK_E_NOT_SPD, "nk_sym_sqrt: matrix is not positive definite (pivot " + std::to_string(host.info) + ")");
     const double nrm = std::sqrt(host.nrm2);   // >= ||L^T||_2
+    double lam_lo = lambda_min_bound;
+    if (estimate) {
+        double lam_est = 1e300;
+        for (int r = 0; r < kProbeRows; r++)
+            if (host.probe[kProbeRows + r] > 0.0 && std::isfinite(host.probe[kProbeRows + r])) lam_est = std::min(lam_est, host.probe[r] / host.probe[kProbeRows + r]);
+        if (lam_est < 1e300 && 0.25 * lam_est > lam_lo) lam_lo = 0.25 * lam_est;
+    }
     dim3 grid, block; launch2d(n, n, grid, block);
     scale_copy_kernel<<<grid, block, 0, stream>>>(n, n, 1.0 / nrm, Lt, ldn, X, ldn);
     scale_copy_kernel<<<grid, block, 0, stream>>>(n, n, 1.0 / nrm, L, ldn, Xt, ldn);
@@ -736,7 +796,7 @@ int nk_sym_sqrt(nk_handle *h, int n, const double *K, long long ldk, double lamb
 
     // Newton-Schulz polar iteration  X <- (a I - b X X^T) X  with the minimax cubic while the singular-value lower
     // bound l < 1, then plain (1.5, 0.5) steps (quadratic convergence) until l reaches 1 to rounding.
-    double l = 0.9 * std::sqrt(lambda_min_bound) / nrm;
+    double l = 0.9 * std::sqrt(lam_lo) / nrm;
     if (l > 1.0) l = 1.0;
     int it = 0, plain = 0;
     while (it < 100) {
@@ -747,7 +807,19 @@ int nk_sym_sqrt(nk_handle *h, int n, const double *K, long long ldk, double lamb
         gemm_nt(h, n, n, n, 1.0, T, ldn, Xt, ldn, 0.0, X2, ldn, 0.0, kGemmStoreT, Xt2, ldn, stream);
         std::swap(X, X2); std::swap(Xt, Xt2);
         it++;
-        if (plain >= 3) break;
+        if (plain >= 3) {
+            if (!estimate) break;
+            // residual check: the T of this (plain) step was 1.5 I - 0.5 X X^T of the PREVIOUS iterate, so max|T - I| = r/2 with r the
+            // orthogonality residual before the step, and the step squares it: r <= 2e-8 means converged to rounding.
+            NK_CUDA(h, cudaMemsetAsync(dprobe + 2 * kProbeRows, 0, 8, stream));
+            max_dev_identity_kernel<<<n, 256, 0, stream>>>(n, T, ldn, dprobe + 2 * kProbeRows);
+            h->launches++;
+            double resid = 0.0;
+            NK_CUDA(h, cudaMemcpyAsync(&resid, dprobe + 2 * kProbeRows, 8, cudaMemcpyDeviceToHost, stream));
+            NK_CUDA(h, cudaStreamSynchronize(stream));
+            if (resid <= 1e-8 || it >= 60) break;
+            plain = 2;          // not there yet (the estimate was too optimistic): one more plain step, check again
+        }
     }
     if (iters) *iters = it;
     // S = Q^T L^T  ->  S(i,j) = sum_k Xt(i,k) L(j,k); symmetrised

@@ -154,14 +154,19 @@ def test_potrf_not_spd(engine):
         engine.potrf(dev(A))
 
 
-@pytest.mark.parametrize("m,d,kind,ls", [(100, 192, O.RBF, 10.0), (20, 2, O.MATERN52, 1.0), (300, 8, O.RBF, 3.0), (513, 192, O.RBF, 10.0)])
+@pytest.mark.parametrize("m,d,kind,ls", [(100, 192, O.RBF, 10.0), (20, 2, O.MATERN52, 1.0), (300, 8, O.RBF, 3.0), (513, 192, O.RBF, 10.0),
+                                         (1100, 192, O.RBF, 10.0), (1200, 2, O.MATERN52, 1.0), (1500, 6, O.RBF, 1.0)])
 def test_sym_sqrt(engine, m, d, kind, ls):
-    """S = sqrtm(K_mm): same distance to the eigh root as scipy's sqrtm has (the oracle's own floor)."""
+    """S = sqrtm(K_mm): same distance to the eigh root as scipy's sqrtm has (the oracle's own floor).  From m = 1024 the
+    Newton-Schulz schedule starts from an inverse-iteration ESTIMATE of lambda_min (nk_dense.cu) instead of the jitter bound:
+    well-conditioned (RBF l=10: fewer iterations than the 17 of the bound), ill-conditioned (Matern in 2-D: lambda_min ~ jitter)
+    and clustered (RBF l=1 in 6-D: K_mm close to the identity) spectra must all land on the same floor."""
     Xs, U, Y, Z = make_problem(3000, d, 1, m, seed=m)
     lsv = np.full(d, ls)
     Kmm = O.kernel_matrix(Z, Z, kind, lsv) + 1e-6 * np.eye(m)
     S, Sinv = engine.sym_sqrt(dev(Kmm))
     S, Sinv = host(S), host(Sinv)
+    print(f"m={m}: {engine.last_sqrt_iters} Newton-Schulz iterations")
     w, V = np.linalg.eigh(Kmm)
     S0 = (V * np.sqrt(w)) @ V.T
     cond = w[-1] / w[0]
