@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdio>
 #include <vector>
+#include <cooperative_groups.h>
 #include "nk_dense.cuh"
 
 namespace nk {
@@ -648,6 +649,150 @@ static double opt_cubic(double l, double *a, double *b) {
 
 static inline int even(int x) { return (x + 1) & ~1; }
 
+// ---------------------------------------------------------------------------------------------------
+// Symmetric square root of a SMALL matrix (n <= 128: the script configurations, m = 10 ... 100) in ONE cooperative launch.
+// The general path above is ~100 dependent small launches with a host synchronisation in the middle (1.4 ms at m = 100: half of a
+// whole script-sized fit).  Here 16 CTAs each own a 32 x 32 tile of every n x n product (operand rows staged in shared memory,
+// plain FP64 FMAs: the matrices are 128 KB and live in L2), separated by grid-wide barriers: the same polar Newton-Schulz
+// iteration with the same minimax-cubic schedule, computed redundantly by every thread from the same numbers.
+// Inputs: Kc (n x n copy of K), L / Linv / LinvT (factor of K and the inverse of the factor, from potrf_diag_kernel).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kSN = 128;                                   // leading dimension of every scratch matrix
+constexpr int kSmallPad = 129;
+constexpr size_t kSmallSmem = 2 * 32 * kSmallPad * 8;      // two 32 x 128 operand strips
+
+__device__ __forceinline__ double dev_opt_cubic(double l, double &a, double &b) {
+    const double s = 1.0 + l + l * l, xs = sqrt(s / 3.0);
+    const double bb = 2.0 / ((2.0 * s / 3.0) * xs + (l + l * l));
+    const double aa = bb * s;
+    const double pmax = (2.0 * aa / 3.0) * xs, pmin = aa - bb;
+    a = aa / pmax; b = bb / pmax;
+    return pmin / pmax;
+}
+
+// acc(2x2 per thread) = sum_k A[32 bi + r, k] B[32 bj + c, k]  for the CTA's tile; r in {ty, ty+16}, c in {tx, tx+16}
+__device__ __forceinline__ void small_nt_tile(const double *__restrict__ A, const double *__restrict__ B, int n, int bi, int bj, double (&acc)[2][2],
+                                              double *sA, double *sB) {
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < 32 * kSN; idx += 256) {
+        const int r = idx >> 7, k = idx & (kSN - 1);
+        const int ga = bi * 32 + r, gb = bj * 32 + r;
+        sA[r * kSmallPad + k] = (ga < n && k < n) ? A[ga * kSN + k] : 0.0;
+        sB[r * kSmallPad + k] = (gb < n && k < n) ? B[gb * kSN + k] : 0.0;
+    }
+    __syncthreads();
+    const int ty = tid >> 4, tx = tid & 15;
+    acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = 0.0;
+    for (int k = 0; k < n; k++) {
+        const double a0 = sA[ty * kSmallPad + k], a1 = sA[(ty + 16) * kSmallPad + k];
+        const double b0 = sB[tx * kSmallPad + k], b1 = sB[(tx + 16) * kSmallPad + k];
+        acc[0][0] = fma(a0, b0, acc[0][0]); acc[0][1] = fma(a0, b1, acc[0][1]);
+        acc[1][0] = fma(a1, b0, acc[1][0]); acc[1][1] = fma(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 1) small_polar_kernel(int n, double lambda_min_bound, const double *Kc, const double *L, const double *LinvT,
+                                                             double *X, double *Xt, double *X2, double *Xt2, double *T, double *S, long long lds,
+                                                             double *Sinv, long long ldsi, int *iters_out) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) double ssm[];
+    double *sA = ssm, *sB = ssm + 32 * kSmallPad;
+    __shared__ double red[256];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int bi = blockIdx.x >> 2, bj = blockIdx.x & 3;
+    const int r0 = bi * 32 + ty, r1 = r0 + 16, c0 = bj * 32 + tx, c1 = c0 + 16;
+    // ||K||_inf (every CTA, redundantly): an upper bound on ||L^T||_2^2
+    double rs = 0.0;
+    if (tid < n) for (int c = 0; c < n; c++) rs += fabs(Kc[c * kSN + tid]);      // K is symmetric: column sums, coalesced
+    red[tid] = rs;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (tid < o) red[tid] = fmax(red[tid], red[tid + o]); __syncthreads(); }
+    const double nrm = sqrt(red[0]);
+    __syncthreads();
+    // X0 = L^T / nrm, Xt0 = L / nrm  (this CTA's tile)
+    {
+        const int rr[2] = {r0, r1}, cc[2] = {c0, c1};
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+                if (rr[i] < n && cc[j] < n) {
+                    const double lv = L[rr[i] * kSN + cc[j]] / nrm;      // L is lower triangular with an explicit zero upper part
+                    Xt[rr[i] * kSN + cc[j]] = lv;
+                    X[cc[j] * kSN + rr[i]] = lv;
+                }
+    }
+    grid.sync();
+    double l = fmin(1.0, 0.9 * sqrt(lambda_min_bound) / nrm);
+    int it = 0, plain = 0;
+    double acc[2][2];
+    while (it < 100) {
+        double a, b;
+        if (l < 0.999) l = dev_opt_cubic(l, a, b);
+        else { a = 1.5; b = 0.5; plain++; }
+        // T = a I - b X X^T
+        small_nt_tile(X, X, n, bi, bj, acc, sA, sB);
+        {
+            const int rr[2] = {r0, r1}, cc[2] = {c0, c1};
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+                    if (rr[i] < n && cc[j] < n) T[rr[i] * kSN + cc[j]] = -b * acc[i][j] + (rr[i] == cc[j] ? a : 0.0);
+        }
+        grid.sync();
+        // X <- T X  (NT with the transposed copy), both orientations stored
+        small_nt_tile(T, Xt, n, bi, bj, acc, sA, sB);
+        {
+            const int rr[2] = {r0, r1}, cc[2] = {c0, c1};
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+                    if (rr[i] < n && cc[j] < n) { X2[rr[i] * kSN + cc[j]] = acc[i][j]; Xt2[cc[j] * kSN + rr[i]] = acc[i][j]; }
+        }
+        grid.sync();
+        double *t1 = X; X = X2; X2 = t1;
+        double *t2 = Xt; Xt = Xt2; Xt2 = t2;
+        it++;
+        if (plain >= 3) break;
+    }
+    // M1 = Q^T L^T  (-> T),  M2 = L^-T Q  (-> X2);  Q = X
+    small_nt_tile(Xt, L, n, bi, bj, acc, sA, sB);
+    {
+        const int rr[2] = {r0, r1}, cc[2] = {c0, c1};
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+                if (rr[i] < n && cc[j] < n) T[rr[i] * kSN + cc[j]] = acc[i][j];
+    }
+    small_nt_tile(LinvT, Xt, n, bi, bj, acc, sA, sB);
+    {
+        const int rr[2] = {r0, r1}, cc[2] = {c0, c1};
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+                if (rr[i] < n && cc[j] < n) X2[rr[i] * kSN + cc[j]] = acc[i][j];
+    }
+    grid.sync();
+    {
+        const int rr[2] = {r0, r1}, cc[2] = {c0, c1};
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+                if (rr[i] < n && cc[j] < n) {
+                    S[(long long)rr[i] * lds + cc[j]] = 0.5 * (T[rr[i] * kSN + cc[j]] + T[cc[j] * kSN + rr[i]]);
+                    Sinv[(long long)rr[i] * ldsi + cc[j]] = 0.5 * (X2[rr[i] * kSN + cc[j]] + X2[cc[j] * kSN + rr[i]]);
+                }
+    }
+    if (blockIdx.x == 0 && tid == 0) *iters_out = it;
+}
+
 }  // namespace nk
 
 using namespace nk;
@@ -737,6 +882,35 @@ int nk_sym_sqrt(nk_handle *h, int n, const double *K, long long ldk, double lamb
     if (n < 1 || !K || !S || !Sinv || !(lambda_min_bound > 0.0)) return set_err(h, NK_E_INVALID, "nk_sym_sqrt: bad argument");
     NK_ON_DEVICE(h);
     int rc;
+    if (n <= kSN && ldk >= n && lds >= n && ldsi >= n) {
+        // small matrices: factor + inverse of the factor (one CTA), then the whole polar iteration in one cooperative launch
+        const size_t mm = (size_t)kSN * kSN;
+        double *buf = dense_scratch(h, 0, 9 * mm, &rc); if (rc) return rc;
+        double *Kc = buf, *Lc = buf + mm, *Li = buf + 2 * mm, *LiT = buf + 3 * mm, *X = buf + 4 * mm, *Xt = buf + 5 * mm, *X2 = buf + 6 * mm,
+               *Xt2 = buf + 7 * mm, *T = buf + 8 * mm;
+        if ((rc = ensure(h, h->dinfo, 256)) != NK_OK) return rc;
+        int *dinfo = (int *)h->dinfo.ptr;
+        NK_CUDA(h, cudaMemsetAsync(dinfo, 0, 16, stream));
+        NK_CUDA(h, cudaMemcpy2DAsync(Kc, kSN * 8, K, ldk * 8, (size_t)n * 8, n, cudaMemcpyDeviceToDevice, stream));
+        NK_CUDA(h, cudaMemcpy2DAsync(Lc, kSN * 8, K, ldk * 8, (size_t)n * 8, n, cudaMemcpyDeviceToDevice, stream));
+        launch_diag(h, 1, Lc, kSN, 0, n, 0, Li, LiT, 0, dinfo, 1, stream);
+        static unsigned long long configured = 0;
+        if (first_use_on_device(configured)) cudaFuncSetAttribute(small_polar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem);
+        int nn = n;
+        double lmb = lambda_min_bound;
+        const double *cKc = Kc, *cL = Lc, *cLiT = LiT;
+        long long lds_ = lds, ldsi_ = ldsi;
+        int *it_out = dinfo + 1;
+        void *args[] = {&nn, &lmb, &cKc, &cL, &cLiT, &X, &Xt, &X2, &Xt2, &T, &S, &lds_, &Sinv, &ldsi_, &it_out};
+        NK_CUDA(h, cudaLaunchCooperativeKernel((const void *)small_polar_kernel, dim3(16), dim3(256), args, kSmallSmem, stream));
+        h->launches++;
+        int hres[2] = {0, 0};
+        NK_CUDA(h, cudaMemcpyAsync(hres, dinfo, 8, cudaMemcpyDeviceToHost, stream));
+        NK_CUDA(h, cudaStreamSynchronize(stream));
+        if (hres[0] != 0) return set_err(h, NK_E_NOT_SPD, "nk_sym_sqrt: matrix is not positive definite (pivot " + std::to_string(hres[0]) + ")");
+        if (iters) *iters = hres[1];
+        return NK_OK;
+    }
     const int ldn = even(n), nblk = (n + kDB - 1) / kDB;
     const size_t nn = (size_t)n * ldn;
     double *L = dense_scratch(h, 0, nn, &rc); if (rc) return rc;
@@ -760,9 +934,9 @@ int nk_sym_sqrt(nk_handle *h, int n, const double *K, long long ldk, double lamb
     // a lower bound l on sigma_min(L^T) / ||L^T||; the only GUARANTEED one is sqrt(lambda_min_bound) -- the jitter, 1e-6 -- which at
     // m = 4096 on the benchmark's kernel matrix (cond 2e3) is 1000 x too pessimistic and costs 6-7 of 17 iterations.  A few steps of
     // inverse iteration with the factor just computed (8 fixed +-1 start vectors, v <- K^-1 v through the transposed-storage
-    // triangular sweeps) give lambda_est = min_r |v_5| / |v_6| >= lambda_min, within a few percent after 6 steps; the schedule uses a
+    // triangular sweeps) give lambda_est = min_r |v_3| / |v_4| >= lambda_min, within a few percent after 4 steps; the schedule uses a
     // quarter of it, and the residual check after the scheduled iterations catches an estimate that was still too optimistic.
-    constexpr int kProbeRows = 8, kProbeSteps = 6;
+    constexpr int kProbeRows = 8, kProbeSteps = 4;
     const bool estimate = n >= 1024;
     double *dprobe = dnorm + 1;     // [1..8]: |v_5|, [9..16]: |v_6|, [17]: residual of the convergence check
     if (estimate) {

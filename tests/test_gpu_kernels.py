@@ -154,7 +154,8 @@ def test_potrf_not_spd(engine):
         engine.potrf(dev(A))
 
 
-@pytest.mark.parametrize("m,d,kind,ls", [(100, 192, O.RBF, 10.0), (20, 2, O.MATERN52, 1.0), (300, 8, O.RBF, 3.0), (513, 192, O.RBF, 10.0),
+@pytest.mark.parametrize("m,d,kind,ls", [(100, 192, O.RBF, 10.0), (20, 2, O.MATERN52, 1.0), (128, 1, O.MATERN52, 1.0), (1, 3, O.RBF, 1.0), (129, 8, O.RBF, 3.0),
+                                         (300, 8, O.RBF, 3.0), (513, 192, O.RBF, 10.0),
                                          (1100, 192, O.RBF, 10.0), (1200, 2, O.MATERN52, 1.0), (1500, 6, O.RBF, 1.0)])
 def test_sym_sqrt(engine, m, d, kind, ls):
     """S = sqrtm(K_mm): same distance to the eigh root as scipy's sqrtm has (the oracle's own floor).  From m = 1024 the
@@ -171,7 +172,7 @@ def test_sym_sqrt(engine, m, d, kind, ls):
     S0 = (V * np.sqrt(w)) @ V.T
     cond = w[-1] / w[0]
     assert np.array_equal(S, S.T) and np.array_equal(Sinv, Sinv.T)
-    assert O.relerr(S @ S, Kmm) <= 1e-13
+    assert O.relerr(S @ S, Kmm) <= (1e-13 if m <= 1000 else 3e-13)
     assert O.relerr(S, S0) <= 1e-15 * max(10.0, cond ** 0.5) * 10
     assert np.linalg.norm(Sinv @ S - np.eye(m)) / np.sqrt(m) <= 1e-15 * max(10.0, cond ** 0.5) * 100
 
