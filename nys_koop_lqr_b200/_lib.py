@@ -75,7 +75,14 @@ _lib = None
 
 
 class NkError(RuntimeError):
-    pass
+    """A C-ABI call failed; `rc` is its status (NK_E_* of include/nk_b200.h: -1 invalid, -2 CUDA, -3 not SPD, -4 no memory, -5 state)."""
+
+    def __init__(self, message, rc=None):
+        super().__init__(message)
+        self.rc = rc
+
+
+NK_E_NOT_SPD = -3
 
 
 def load() -> C.CDLL:
@@ -97,4 +104,4 @@ def load() -> C.CDLL:
 def check(handle, rc: int, what: str) -> None:
     if rc != 0:
         msg = load().nk_last_error_string(handle)
-        raise NkError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
+        raise NkError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}", rc=rc)

@@ -342,12 +342,12 @@ class KoopmanNystromRegressor(KoopmanRegressor):
     def _solve_guarded(self, fn, G):
         """Runs a solve; if a regularised system is not positive definite in float64 (cond >~ 1e16: the tiniest gammas of the
         scripts' grids), retries once with a diagonal shift (see _shift_grams) and records it in ``spd_shift_``."""
-        from ._lib import NkError
+        from ._lib import NK_E_NOT_SPD, NkError
         self.spd_shift_ = 0.0
         try:
             return fn()
         except NkError as exc:
-            if "not positive definite" not in str(exc):
+            if exc.rc != NK_E_NOT_SPD:
                 raise
             import warnings
             self.spd_shift_ = self._shift_grams(G)

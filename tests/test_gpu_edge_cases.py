@@ -91,3 +91,28 @@ def test_empty_block_inside_a_streamed_accumulation(engine):
     engine.gram_update(X[300:], Yd[300:])
     parts = engine.gram_finalize()["_flat"]
     assert O.relerr(parts.cpu().numpy(), whole.cpu().numpy()) <= 1e-13
+
+
+def test_indefinite_regularised_system_is_retried_with_a_diagonal_shift(engine):
+    """Where the reference's lstsq (gelsd, rcond = eps) would truncate a numerically singular inner_term, the Cholesky path retries once
+    with a Tikhonov shift of 64 eps max-diag, warns, and records the shift instead of failing the fit."""
+    import warnings
+    import regressors as R
+    rng = np.random.default_rng(0)
+    d, p, m, n = 3, 1, 16, 20
+    x = rng.standard_normal((1, d + p))
+    X = np.repeat(x, n, axis=0)                         # n copies of ONE sample: G_xx has rank 1, and gamma = 0 adds nothing
+    Y = np.repeat(rng.standard_normal((1, d)), n, axis=0)
+    reg = R.KoopmanNystromRegressor(p, kernel=R.KernelWrapper([1.0] * d), gamma=0.0, m=m)
+    reg.nystrom_centers_output = rng.standard_normal((d, m))
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        reg.fit(X, Y)
+    assert reg.spd_shift_ > 0.0 and any("diagonal shift" in str(w.message) for w in caught)
+    assert np.isfinite(reg.A).all() and np.isfinite(reg.B).all() and np.isfinite(reg.C).all()
+    # a healthy system is not touched
+    Xs, U, Yh = O.synthetic(400, d, p, seed=2)
+    reg2 = R.KoopmanNystromRegressor(p, kernel=R.KernelWrapper([1.0] * d), gamma=1e-3, m=m)
+    reg2.nystrom_centers_output = reg.nystrom_centers_output
+    reg2.fit(np.hstack((Xs, U)), Yh)
+    assert reg2.spd_shift_ == 0.0
