@@ -13,7 +13,7 @@ def shard_bounds(n_total: int, world: int, rank: int):
     return offset, n_local
 
 
-HEAD_COEFF = 56.0     # m^3-flop equivalents of the landmark-only stage (see head_samples); tools/multi_gpu_round.sh sweeps it
+HEAD_COEFF = 48.0     # m^3-flop equivalents of the landmark-only stage (see head_samples); tools/multi_gpu_round.sh sweeps it
 
 
 def head_samples(m: int, d: int, p: int) -> int:
@@ -21,8 +21,8 @@ def head_samples(m: int, d: int, p: int) -> int:
     iterations of the symmetric square root, S and S^-1: ~56 m^3 flop on the row-major GEMM at ~82% of the DMMA rate, plus the
     packing of the three m x m results for the broadcast, against 4m^2+6md+4mp flop per sample at ~90%).  Calibrated on the
     measurement at m=4096, d=192.  Round 1: 143 ms against 467 k samples/s = 67 k samples (coefficient 64).  Round 2 (TMA-fed GEMM):
-    125 ms against 474 k samples/s = 59 k samples (coefficient 56; with 64 the head finished 17 ms early,
-    profiles/r02_fit_distributed_phases.md).  Overshooting is cheap (the surplus is spread over the other ranks), undershooting
+    125 ms against 474 k samples/s = 59 k samples (coefficient 56), then 107 ms with the spectrum estimate of the symmetric
+    square root = 50 k samples (coefficient 48; profiles/r02_fit_distributed_phases_2gpu.log).  Overshooting is cheap (the surplus is spread over the other ranks), undershooting
     is paid in full."""
     per_sample = 4.0 * m * m + 6.0 * m * d + 4.0 * m * p
     return int(HEAD_COEFF * m ** 3 / per_sample * (0.90 / 0.82))
