@@ -108,7 +108,9 @@ int nk_potrf(nk_handle *h, int n, double *A, long long lda, int *info, void *str
 int nk_trsm_lower(nk_handle *h, int trans, int n, int nrhs, const double *L, long long ldl, double *B, long long ldb, void *stream);
 /* symmetric principal square root S = K^(1/2) and S^-1 of an SPD matrix (scipy.linalg.sqrtm at regressors.py:140,163,175
  * and the solves against it at :152,153,177).  lambda_min_bound > 0: a lower bound on the smallest eigenvalue (the
- * jitter 1e-6 for K_mm).  iters (host int*, may be NULL) receives the Newton-Schulz iteration count. */
+ * jitter 1e-6 for K_mm).  iters (host int*, may be NULL) receives the Newton-Schulz iteration count.
+ * n <= 128 runs as one cooperative launch; from n = 1024 the iteration schedule starts from an inverse-iteration ESTIMATE of
+ * lambda_min (never below lambda_min_bound) and a residual check adds steps if the estimate was too optimistic.  Synchronises `stream`. */
 int nk_sym_sqrt(nk_handle *h, int n, const double *K, long long ldk, double lambda_min_bound,
                 double *S, long long lds, double *Sinv, long long ldsi, int *iters, void *stream);
 
