@@ -755,8 +755,9 @@ class KoopmanNystromRegressor(KoopmanRegressor):
         d, N = X.shape
         dev = self._device_state(d)
         eng = dev["eng"]
-        out = np.empty((self.m, N))
-        step = max(1, int(2 ** 27 // max(self.m, 1)))
+        m = int(dev["Z"].shape[0])                       # not self.m: centres may have been injected without a fit
+        out = np.empty((m, N))
+        step = max(1, int(2 ** 27 // max(m, 1)))
         for s in range(0, N, step):
             e = min(N, s + step)
             rows = torch.from_numpy(np.ascontiguousarray(X[:, s:e].T)).to(eng.tdev)
@@ -776,7 +777,7 @@ class KoopmanNystromRegressor(KoopmanRegressor):
             W = torch.from_numpy(np.ascontiguousarray(np.asarray(self.weights, dtype=np.float64))).to(eng.tdev)
             dev["W"] = W
         out = np.empty((N, d))
-        step = max(1, int(2 ** 27 // max(self.m, 1)))
+        step = max(1, int(2 ** 27 // max(int(dev["Z"].shape[0]), 1)))
         for s in range(0, N, step):
             e = min(N, s + step)
             rows = torch.from_numpy(X_aug[s:e]).to(eng.tdev)

@@ -116,3 +116,29 @@ def test_indefinite_regularised_system_is_retried_with_a_diagonal_shift(engine):
     reg2.nystrom_centers_output = reg.nystrom_centers_output
     reg2.fit(np.hstack((Xs, U)), Yh)
     assert reg2.spd_shift_ == 0.0
+
+
+def test_lift_with_injected_centres_and_no_m(engine):
+    """`lift` only needs the centres and the kernel (regressors.py:171-178 never reads self.m): an estimator built with m=None whose
+    centres were assigned by hand lifts and, given weights, predicts -- also after a pickle round trip (device cache is not pickled)."""
+    import pickle
+    import regressors as R
+    rng = np.random.default_rng(3)
+    d, p, m, N = 4, 2, 11, 37
+    Zc = rng.standard_normal((d, m))
+    lsv = np.array([0.9, 1.1, 1.3, 0.7])
+    reg = R.KoopmanNystromRegressor(p, kernel=R.KernelWrapper(list(lsv)), gamma=1e-3)
+    assert reg.m is None
+    reg.nystrom_centers_output = Zc
+    reg.nystrom_centers_input = Zc
+    X = rng.standard_normal((d, N))
+    got = reg.lift(X)
+    want = O.lift(np.ascontiguousarray(Zc.T), X, O.MATERN52, lsv)
+    assert got.shape == (m, N)
+    assert O.relerr(got, want) <= 1e-9
+    reg.weights = rng.standard_normal((d, m + p))
+    Xa = np.hstack((X.T, rng.standard_normal((N, p))))
+    pred = reg.predict(Xa)
+    assert O.relerr(pred, (reg.weights @ np.vstack((got, Xa[:, d:].T))).T) <= 1e-12
+    clone = pickle.loads(pickle.dumps(reg))
+    assert O.relerr(clone.predict(Xa), pred) <= 1e-14
