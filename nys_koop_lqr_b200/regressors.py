@@ -179,7 +179,8 @@ class KoopmanNystromRegressor(KoopmanRegressor):
     fit(X (n, d+p), Y (n, d)) -> None; lift(X (d, N)) -> (m, N); predict(X_aug (N, d+p)) -> (N, d).
     After fit: A (m,m), B (m,p), C (d,m), weights (d, m+p) are numpy float64; centres are (d, m) like upstream.
     Additive API: ``forecast`` (batched open-loop rollout), ``fit_cv`` (batched grid search), ``fit_distributed`` (sample-sharded fit, one NCCL
-    allreduce of the Grams), ``stream_block`` (rows per host->device block of the streaming fit).
+    allreduce of the Grams), ``closed_loop`` / ``lqr_closed_loop`` (the scripts' ``lqr_control`` loops), ``lqr_gain`` (``control.dlqr`` on the
+    device), ``stream_block`` (rows per host->device block of the streaming fit).
     """
 
     stream_block = 262144     # samples per host->device block when inputs live in host memory
@@ -893,6 +894,37 @@ def _lqr_closed_loop(self, K, initial_state, reference, num_steps, step):
 
 
 KoopmanNystromRegressor.lqr_closed_loop = _lqr_closed_loop
+
+
+def _lqr_gain(self, Q=None, R=None, q_scale=1.0, return_all=False):
+    """LQR gain of the fitted lifted model, on the device: ``control.dlqr(A, B, Q, R)[0]`` of the scripts with their defaults
+    Q = q_scale * C'C symmetrised (benchmark_lqr_cloth.py:239-240 uses 0.0075, _classic.py:284 and _hjb.py:289 use 1) and
+    R = I (p x p).  The Riccati equation is solved by doubling (``nys_koop_lqr_b200/dare.py``): m x m products on the FP64
+    tensor-core GEMM, so a gain at m = 4096-8192 costs about a second where scipy's QZ-based solver needs the better part of an
+    hour.  Returns K (p, m) numpy; with ``return_all`` also the Riccati solution P (m, m) and the
+    iteration record dict(iterations, delta, residual)."""
+    import torch
+    from . import dare
+    eng = self.__dict__["_dev"]["eng"] if self.__dict__.get("_dev") else _engine()
+    pend = self.__dict__.get("_pending") or {}
+    dev_of = lambda name: pend[name] if name in pend else torch.from_numpy(
+        np.ascontiguousarray(np.asarray(getattr(self, name), dtype=np.float64))).to(eng.tdev)
+    A, B, C = dev_of("A"), dev_of("B"), dev_of("C")
+    ops = dare.EngineOps(eng)
+    m, p = A.shape[0], B.shape[1]
+    if Q is None:
+        Qd = ops.mm(C, C, ta=True) * float(q_scale)
+    else:
+        Qd = torch.from_numpy(np.ascontiguousarray(np.asarray(Q, dtype=np.float64))).to(eng.tdev)
+    Rd = (torch.eye(p, dtype=torch.float64, device=eng.tdev) if R is None
+          else torch.from_numpy(np.ascontiguousarray(np.atleast_2d(np.asarray(R, dtype=np.float64)))).to(eng.tdev))
+    P, info = dare.solve_dare(A, B.contiguous(), Qd, Rd, ops=ops)
+    K = dare.gain_from_solution(A, B.contiguous(), Rd, P, ops).cpu().numpy()
+    self.lqr_info_ = info
+    return (K, P.cpu().numpy(), info) if return_all else K
+
+
+KoopmanNystromRegressor.lqr_gain = _lqr_gain
 
 
 # ----------------------------------------------------------------------------------------------
