@@ -1,7 +1,7 @@
 """Discrete-time algebraic Riccati equation and LQR gain on the device: ``control.dlqr(A, B, Q, R)`` of the reference's
 scripts (benchmark_lqr_cloth.py:262, benchmark_lqr_classic.py:288, benchmark_lqr_hjb.py:293,356) for lifted models whose
 dimension m makes the host solver (python-control -> scipy ``solve_discrete_are``: a QZ decomposition of a 2m x 2m pencil,
-minutes at m = 4096) the slowest step after the fit.  SURVEY.md section 8(f), row 4.
+14 s at m = 500, hours at m = 4096) by far the slowest step after the fit.  SURVEY.md section 8(f), row 4.
 
 Method: the structure-preserving doubling algorithm for
 

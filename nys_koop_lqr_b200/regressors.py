@@ -900,8 +900,8 @@ def _lqr_gain(self, Q=None, R=None, q_scale=1.0, return_all=False):
     """LQR gain of the fitted lifted model, on the device: ``control.dlqr(A, B, Q, R)[0]`` of the scripts with their defaults
     Q = q_scale * C'C symmetrised (benchmark_lqr_cloth.py:239-240 uses 0.0075, _classic.py:284 and _hjb.py:289 use 1) and
     R = I (p x p).  The Riccati equation is solved by doubling (``nys_koop_lqr_b200/dare.py``): m x m products on the FP64
-    tensor-core GEMM, so a gain at m = 4096-8192 costs about a second where scipy's QZ-based solver needs the better part of an
-    hour.  Returns K (p, m) numpy; with ``return_all`` also the Riccati solution P (m, m) and the
+    tensor-core GEMM, so a gain at m = 4096-8192 costs about a second where scipy's QZ-based solver needs hours
+    (SURVEY 8f row 4).  Returns K (p, m) numpy; with ``return_all`` also the Riccati solution P (m, m) and the
     iteration record dict(iterations, delta, residual)."""
     import torch
     from . import dare
