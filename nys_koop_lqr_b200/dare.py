@@ -29,7 +29,9 @@ from ._lib import NkError
 
 
 class TorchOps:
-    """Dense products and solves through torch on whatever device the operands live on (the CPU statement of the ops)."""
+    """Dense products and solves through torch on whatever device the operands live on: the statement of the ops that the CPU test
+    suite runs.  Never chosen implicitly -- every function below takes ``ops`` explicitly, and ``dlqr`` / ``reg.lqr_gain`` build
+    ``EngineOps`` (which raises without the library and a GPU)."""
 
     def mm(self, A, B, ta=False, tb=False):
         return (A.T if ta else A) @ (B.T if tb else B)
@@ -75,12 +77,11 @@ def _sym(M):
     return (M + M.T) * 0.5
 
 
-def solve_dare(A, B, Q, R, ops=None, tol=1e-13, max_iter=64):
+def solve_dare(A, B, Q, R, ops, tol=1e-13, max_iter=64):
     """Stabilising solution P of the DARE by doubling.  A (m,m), B (m,p), Q (m,m) symmetric PSD, R (p,p) symmetric PD: float64
     torch tensors on one device.  Returns (P, info) with info = dict(iterations, delta (last relative change of H),
     residual (relative DARE residual of the returned P)).  Raises NkError if the iteration has not settled after ``max_iter``
     doublings or produced non-finite values ((A, B) not stabilisable / (A, Q) not detectable)."""
-    ops = ops or TorchOps()
     m, p = B.shape
     if A.shape != (m, m) or Q.shape != (m, m) or R.shape != (p, p):
         raise ValueError("solve_dare: A (m,m), B (m,p), Q (m,m), R (p,p) expected")
@@ -111,17 +112,15 @@ def solve_dare(A, B, Q, R, ops=None, tol=1e-13, max_iter=64):
     return H, dict(iterations=it, delta=delta, residual=dare_residual(A, B, Q, R, H, ops))
 
 
-def gain_from_solution(A, B, R, P, ops=None):
+def gain_from_solution(A, B, R, P, ops):
     """K = (R + B' P B)^-1 B' P A, (p, m): the first return value of control.dlqr."""
-    ops = ops or TorchOps()
     PB = ops.mm(P, B)                                                # (m, p)
     M = _sym(R + ops.mm(B, PB, ta=True))
     return ops.spd_solve(M, ops.mm(PB, A, ta=True))
 
 
-def dare_residual(A, B, Q, R, P, ops=None):
+def dare_residual(A, B, Q, R, P, ops):
     """|| A'PA - A'PB (R + B'PB)^-1 B'PA + Q - P ||_F / || P ||_F."""
-    ops = ops or TorchOps()
     PA = ops.mm(P, A)
     K = gain_from_solution(A, B, R, P, ops)
     res = ops.mm(A, PA, ta=True) - ops.mm(ops.mm(PA, B, ta=True), K) + _sym(Q) - P       # (PA)'B = A'PB, P symmetric

@@ -80,7 +80,7 @@ def test_not_stabilisable_is_an_error_not_a_wrong_gain():
         _cpu_dlqr(A, B, np.eye(2), np.eye(1))
     with pytest.raises(ValueError):
         dare.solve_dare(torch.eye(3, dtype=torch.float64), torch.ones(3, 1, dtype=torch.float64),
-                        torch.eye(2, dtype=torch.float64), torch.eye(1, dtype=torch.float64))
+                        torch.eye(2, dtype=torch.float64), torch.eye(1, dtype=torch.float64), dare.TorchOps())
 
 
 def test_engine_ops_only_override_the_products_and_the_spd_solve():
